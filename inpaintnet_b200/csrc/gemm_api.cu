@@ -1,0 +1,116 @@
+// ipn_gemm: universal GEMM + fused epilogue (see include/inpaintnet_b200.h).
+#include "launch.cuh"
+
+namespace ipn {
+
+static int fill_linear_epi(EpiLinear::Params& e, const IpnGemm* g) {
+  e.out = g->out;
+  e.out_dt = g->out_dt;
+  e.ld_out = g->ld_out;
+  e.use_rowmap = g->use_rowmap;
+  e.rowmap = g->rowmap;
+  e.split_cols = g->split_cols;
+  e.split_stride = g->split_stride;
+  e.bias = g->bias;
+  e.act = g->act;
+  e.alpha = g->alpha;
+  e.mul_src = g->mul_src;
+  e.mul_dt = g->mul_dt;
+  e.ld_mul = g->ld_mul;
+  e.mul_mode = g->mul_mode;
+  e.mul_scale = g->mul_scale;
+  e.accumulate = g->accumulate;
+  return IPN_OK;
+}
+
+template <int BNG, bool TA, bool TB>
+static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
+  using Cfg = UmmaCfg<1, BNG, TA, TB>;
+  UmmaBatch<EpiLinear> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = split_k;
+  UmmaProblem<EpiLinear>& P = b.p[0];
+  P.nseg = g->nseg;
+  P.M = g->M;
+  P.N = g->N;
+  P.gate_stride = 0;
+  for (int s = 0; s < g->nseg; ++s) {
+    const IpnGemmSeg& sg = g->seg[s];
+    HostOperand a{sg.A, sg.lda, sg.transA, g->M, 0, 0};
+    HostOperand bb{sg.B, sg.ldb, sg.transB, g->N, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[s], a, bb, sg.K, BNG));
+  }
+  fill_linear_epi(P.epi, g);
+  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream);
+}
+
+static int pick_split_k(const IpnGemm* g, int tile_m, int tile_n, int bk) {
+  if (g->split_k > 0) return g->split_k;
+  if (g->accumulate != IPN_ATOMIC_ADD) return 1;
+  long long tiles = (long long)cdiv(g->M, tile_m) * cdiv(g->N, tile_n);
+  long long chunks = 0;
+  for (int s = 0; s < g->nseg; ++s) chunks += cdiv(g->seg[s].K, bk);
+  int split = 1;
+  while (tiles * split < 2 * 148 && chunks / (split * 2) >= 8 && split < 64) split *= 2;
+  return split;
+}
+
+}  // namespace ipn
+
+using namespace ipn;
+
+extern "C" int ipn_gemm(const IpnGemm* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(g != nullptr, IPN_ERR_ARG, "ipn_gemm: null descriptor");
+  IPN_PROPAGATE(ensure_device());
+  IPN_REQUIRE(g->M > 0 && g->N > 0, IPN_ERR_ARG, "ipn_gemm: empty problem M=%d N=%d", g->M, g->N);
+  IPN_REQUIRE(g->nseg == 1 || g->nseg == 2, IPN_ERR_ARG, "ipn_gemm: nseg must be 1 or 2");
+  IPN_REQUIRE(g->out != nullptr, IPN_ERR_ARG, "ipn_gemm: null output");
+  for (int s = 0; s < g->nseg; ++s)
+    IPN_REQUIRE(g->seg[s].A && g->seg[s].B && g->seg[s].K > 0, IPN_ERR_ARG, "ipn_gemm: bad segment %d", s);
+  IPN_REQUIRE(g->accumulate != IPN_ATOMIC_ADD || g->out_dt == IPN_F32, IPN_ERR_ARG,
+              "ipn_gemm: atomic accumulation needs an fp32 output");
+  IPN_REQUIRE(g->split_k <= 1 || g->accumulate == IPN_ATOMIC_ADD, IPN_ERR_ARG, "ipn_gemm: split_k needs atomic accumulate");
+  IPN_REQUIRE(g->split_cols == 0 || g->split_cols % 16 == 0, IPN_ERR_ARG, "ipn_gemm: split_cols must be a multiple of 16");
+  IPN_REQUIRE(!(g->split_k > 1 && (g->bias || g->act != IPN_ACT_NONE)), IPN_ERR_ARG,
+              "ipn_gemm: bias/activation cannot be combined with split_k");
+
+  if (g->core == IPN_CORE_SIMT) {
+    SimtBatch<EpiLinear> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = pick_split_k(g, SIMT_BM, SIMT_BN, SIMT_BK);
+    if (b.split_k > 1) IPN_REQUIRE(!g->bias && g->act == IPN_ACT_NONE, IPN_ERR_ARG, "split_k with bias/act");
+    SimtProblem<EpiLinear>& P = b.p[0];
+    P.nseg = g->nseg;
+    P.M = g->M;
+    P.N = g->N;
+    P.gate_stride = 0;
+    P.in_dt = g->in_dt;
+    for (int s = 0; s < g->nseg; ++s) {
+      const IpnGemmSeg& sg = g->seg[s];
+      HostOperand a{sg.A, sg.lda, sg.transA, g->M, 0, 0};
+      HostOperand bb{sg.B, sg.ldb, sg.transB, g->N, 0, 0};
+      fill_simt_seg(P.seg[s], a, bb, sg.K, g->in_dt);
+    }
+    fill_linear_epi(P.epi, g);
+    return launch_simt<EpiLinear>(b, 1, g->M, g->N, stream);
+  }
+
+  IPN_REQUIRE(g->core == IPN_CORE_UMMA, IPN_ERR_ARG, "ipn_gemm: unknown core %d", g->core);
+  IPN_REQUIRE(g->in_dt == IPN_BF16, IPN_ERR_ARG, "ipn_gemm: the tcgen05 core takes bf16 operands");
+  const int tA = g->seg[0].transA, tB = g->seg[0].transB;
+  for (int s = 1; s < g->nseg; ++s)
+    IPN_REQUIRE(g->seg[s].transA == tA && g->seg[s].transB == tB, IPN_ERR_ARG, "ipn_gemm: segments must share layouts");
+  const int tn = (!tA && !tB) ? (g->N <= 64 ? 64 : (g->N >= 512 ? 256 : 128)) : 128;
+  const int split = pick_split_k(g, UMMA_BM, tn, UMMA_BK);
+  if (split > 1) IPN_REQUIRE(!g->bias && g->act == IPN_ACT_NONE, IPN_ERR_ARG, "split_k with bias/act");
+  if (!tA && !tB) {
+    if (tn == 64) return gemm_umma<64, false, false>(g, split, stream);
+    if (tn == 256) return gemm_umma<256, false, false>(g, split, stream);
+    return gemm_umma<128, false, false>(g, split, stream);
+  }
+  if (!tA && tB) return gemm_umma<128, false, true>(g, split, stream);
+  if (tA && tB) return gemm_umma<128, true, true>(g, split, stream);
+  ipn::set_error("ipn_gemm: layout transA=1,transB=0 is not provided by the tcgen05 core");
+  return IPN_ERR_ARG;
+}

@@ -1,0 +1,213 @@
+// GRU layer forward / backward drivers: one fused kernel per timestep (recurrent GEMM + gate math
+// in the epilogue), all directions of the layer in the same launch.
+#include "launch.cuh"
+
+namespace ipn {
+
+template <int W>
+__global__ void gru_bwd_point_kernel(GruBwdPoint p0, GruBwdPoint p1, int nrows) {
+  const GruBwdPoint& p = blockIdx.z == 0 ? p0 : p1;
+  const int chunks = (p.H + W - 1) / W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nrows * chunks) return;
+  const int row = (int)(idx / chunks);
+  const int col0 = (int)(idx % chunks) * W;
+  float dh[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) dh[i] = 0.f;
+  gru_bwd_pointwise<W>(p, row, col0, min(W, p.H - col0), dh);
+}
+
+static inline const char* slot_ptr(const void* base, long long slot, long long B_total, int H, int dt) {
+  return reinterpret_cast<const char*>(base) + slot * B_total * H * (dt == IPN_BF16 ? 2 : 4);
+}
+
+static int check_layer_common(int core, int act_dt, int T, int B_total, int H, int row0, int nrows, int ndir) {
+  IPN_REQUIRE(core == IPN_CORE_SIMT || core == IPN_CORE_UMMA, IPN_ERR_ARG, "gru: unknown core %d", core);
+  IPN_REQUIRE(act_dt == IPN_F32 || act_dt == IPN_BF16, IPN_ERR_ARG, "gru: bad act dtype");
+  IPN_REQUIRE(core != IPN_CORE_UMMA || act_dt == IPN_BF16, IPN_ERR_ARG, "gru: the tcgen05 core needs bf16 activations");
+  IPN_REQUIRE(T > 0 && B_total > 0 && H > 0, IPN_ERR_ARG, "gru: bad sizes T=%d B=%d H=%d", T, B_total, H);
+  IPN_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= B_total, IPN_ERR_ARG, "gru: bad row window");
+  IPN_REQUIRE(ndir == 1 || ndir == 2, IPN_ERR_ARG, "gru: ndir must be 1 or 2");
+  IPN_REQUIRE(core != IPN_CORE_UMMA || H % 8 == 0, IPN_ERR_ALIGN, "gru: tcgen05 core needs H %% 8 == 0 (H=%d)", H);
+  return IPN_OK;
+}
+
+}  // namespace ipn
+
+using namespace ipn;
+
+extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "gru_layer_fwd: null descriptor");
+  IPN_PROPAGATE(ensure_device());
+  IPN_PROPAGATE(check_layer_common(L->core, L->act_dt, L->T, L->B_total, L->H, L->row0, L->nrows, L->ndir));
+  IPN_REQUIRE(0 <= L->s_begin && L->s_begin < L->s_end && L->s_end <= L->T, IPN_ERR_ARG, "gru_layer_fwd: bad step range");
+  const int T = L->T, H = L->H, dt = L->act_dt;
+  const long long Bt = L->B_total;
+  for (int d = 0; d < L->ndir; ++d) {
+    const IpnGruDir& D = L->dir[d];
+    IPN_REQUIRE(D.w_hh && D.b_hh && D.hseq, IPN_ERR_ARG, "gru_layer_fwd: null weight/state pointer (dir %d)", d);
+    IPN_REQUIRE(D.P || D.table || D.pvec, IPN_ERR_ARG, "gru_layer_fwd: no input projection source (dir %d)", d);
+    IPN_REQUIRE(!D.table || D.tok, IPN_ERR_ARG, "gru_layer_fwd: table without tokens");
+  }
+
+  auto fill_epi = [&](EpiGruFwd::Params& e, const IpnGruDir& D, int s) {
+    const int t = D.reverse ? T - 1 - s : s;
+    const int in_slot = D.reverse ? t + 1 : t, out_slot = D.reverse ? t : t + 1;
+    e.H = H; e.act_dt = dt; e.row0 = L->row0; e.trow = (long long)t * Bt;
+    e.P = D.P; e.ldP = D.ldP; e.P_bcast = D.P_bcast; e.table = D.table; e.ld_table = D.ld_table; e.tok = D.tok; e.pvec = D.pvec;
+    e.b_hh = D.b_hh;
+    e.h_prev = slot_ptr(D.hseq, in_slot, Bt, H, dt);
+    e.h_out = const_cast<char*>(slot_ptr(D.hseq, out_slot, Bt, H, dt));
+    e.gates = D.gates;
+    e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = D.y_col0; e.mask = L->mask; e.ld_mask = L->ld_mask;
+    e.mask_scale = L->mask_scale;
+    const bool last = (s == T - 1);
+    e.final_out = last ? L->final_out : nullptr;
+    e.final_dt = L->final_dt; e.ld_final = L->ld_final; e.final_col0 = D.final_col0;
+    return in_slot;
+  };
+
+  if (L->core == IPN_CORE_SIMT) {
+    SimtBatch<EpiGruFwd> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
+    for (int s = L->s_begin; s < L->s_end; ++s) {
+      for (int d = 0; d < L->ndir; ++d) {
+        const IpnGruDir& D = L->dir[d];
+        SimtProblem<EpiGruFwd>& P = b.p[d];
+        P.nseg = 1; P.M = L->nrows; P.N = H; P.gate_stride = H; P.in_dt = dt;
+        const int in_slot = fill_epi(P.epi, D, s);
+        HostOperand a{D.hseq, H, 0, (long long)(T + 1) * Bt, in_slot * Bt + L->row0, 0};
+        HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
+        fill_simt_seg(P.seg[0], a, w, H, dt);
+      }
+      IPN_PROPAGATE(launch_simt<EpiGruFwd>(b, L->ndir, L->nrows, H, stream));
+    }
+    return IPN_OK;
+  }
+
+  using Cfg = UmmaCfg<3, 64, false, false>;
+  UmmaBatch<EpiGruFwd> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  for (int d = 0; d < L->ndir; ++d) {
+    const IpnGruDir& D = L->dir[d];
+    UmmaProblem<EpiGruFwd>& P = b.p[d];
+    P.nseg = 1; P.M = L->nrows; P.N = H; P.gate_stride = H;
+    HostOperand a{D.hseq, H, 0, (long long)(T + 1) * Bt, 0, 0};
+    HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BNG));
+  }
+  for (int s = L->s_begin; s < L->s_end; ++s) {
+    for (int d = 0; d < L->ndir; ++d) {
+      const int in_slot = fill_epi(b.p[d].epi, L->dir[d], s);
+      b.p[d].seg[0].a_c1 = (int)(in_slot * Bt + L->row0);
+    }
+    IPN_PROPAGATE((launch_umma<Cfg, EpiGruFwd>(b, L->ndir, L->nrows, H, stream)));
+  }
+  return IPN_OK;
+}
+
+extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "gru_layer_bwd: null descriptor");
+  IPN_PROPAGATE(ensure_device());
+  IPN_PROPAGATE(check_layer_common(L->core, L->act_dt, L->T, L->B_total, L->H, L->row0, L->nrows, L->ndir));
+  IPN_REQUIRE(L->dhz_ws != nullptr, IPN_ERR_ARG, "gru_layer_bwd: null workspace");
+  const int T = L->T, H = L->H, dt = L->act_dt;
+  const long long Bt = L->B_total;
+  for (int d = 0; d < L->ndir; ++d) {
+    const IpnGruBwdDir& D = L->dir[d];
+    IPN_REQUIRE(D.w_hh && D.hseq && D.gates && D.dP && D.dGn, IPN_ERR_ARG, "gru_layer_bwd: null pointer (dir %d)", d);
+  }
+  auto dhz_buf = [&](int d, int which) { return L->dhz_ws + ((long long)d * 2 + which) * Bt * H; };
+
+  // describes the pointwise differentiation of processing step s for direction d
+  auto fill_point = [&](GruBwdPoint& p, int d, int s) {
+    const IpnGruBwdDir& D = L->dir[d];
+    const int t = D.reverse ? T - 1 - s : s;
+    const int in_slot = D.reverse ? t + 1 : t;
+    p.H = H; p.act_dt = dt; p.row0 = L->row0; p.trow = (long long)t * Bt;
+    p.gates = D.gates;
+    p.h_prev = slot_ptr(D.hseq, in_slot, Bt, H, dt);
+    p.dY = L->dY; p.ld_dy = L->ld_dy; p.y_col0 = D.y_col0; p.mask = L->mask; p.ld_mask = L->ld_mask;
+    p.mask_scale = L->mask_scale;
+    p.dh_n = (s == T - 1) ? D.dh_n : nullptr;
+    p.ld_dhn = D.ld_dhn;
+    p.dP = D.dP; p.dGn = D.dGn;
+    p.dhz_out = dhz_buf(d, s & 1);
+  };
+
+  // start of the chain: pointwise for the last processed step
+  {
+    GruBwdPoint p0, p1;
+    fill_point(p0, 0, T - 1);
+    if (L->ndir > 1) fill_point(p1, 1, T - 1); else p1 = p0;
+    constexpr int W = 4;
+    const long long work = (long long)L->nrows * ((H + W - 1) / W);
+    dim3 grid(cdiv(work, 256), 1, L->ndir);
+    gru_bwd_point_kernel<W><<<grid, 256, 0, stream>>>(p0, p1, L->nrows);
+    IPN_LAUNCH_CHECK();
+  }
+
+  auto fill_epi = [&](EpiGruBwd::Params& e, int d, int s) {
+    const IpnGruBwdDir& D = L->dir[d];
+    e.dhz_in = dhz_buf(d, s & 1);
+    e.is_first_step = (s == 0);
+    e.dh0 = D.dh0; e.dh0_dt = D.dh0_dt; e.ld_dh0 = D.ld_dh0; e.dh0_selu = D.dh0_selu;
+    e.h0 = slot_ptr(D.hseq, D.reverse ? T : 0, Bt, H, dt);
+    if (s > 0) fill_point(e.pw, d, s - 1);
+    else { memset(&e.pw, 0, sizeof(e.pw)); e.pw.H = H; e.pw.act_dt = dt; e.pw.row0 = L->row0; }
+  };
+
+  if (L->core == IPN_CORE_SIMT) {
+    SimtBatch<EpiGruBwd> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
+    for (int s = T - 1; s >= 0; --s) {
+      for (int d = 0; d < L->ndir; ++d) {
+        const IpnGruBwdDir& D = L->dir[d];
+        const int t = D.reverse ? T - 1 - s : s;
+        SimtProblem<EpiGruBwd>& P = b.p[d];
+        P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0; P.in_dt = dt;
+        HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, t * Bt + L->row0, 0};
+        HostOperand w0{D.w_hh, H, 1, H, 0, 0};
+        fill_simt_seg(P.seg[0], a0, w0, 2 * H, dt);
+        HostOperand a1{D.dGn, H, 0, (long long)T * Bt, t * Bt + L->row0, 0};
+        HostOperand w1{D.w_hh, H, 1, H, 0, 2LL * H};
+        fill_simt_seg(P.seg[1], a1, w1, H, dt);
+        fill_epi(P.epi, d, s);
+      }
+      IPN_PROPAGATE(launch_simt<EpiGruBwd>(b, L->ndir, L->nrows, H, stream));
+    }
+    return IPN_OK;
+  }
+
+  using Cfg = UmmaCfg<1, 128, false, true>;
+  UmmaBatch<EpiGruBwd> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  for (int d = 0; d < L->ndir; ++d) {
+    const IpnGruBwdDir& D = L->dir[d];
+    UmmaProblem<EpiGruBwd>& P = b.p[d];
+    P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0;
+    HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, 0, 0};
+    HostOperand w0{D.w_hh, H, 1, H, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a0, w0, 2 * H, Cfg::BNG));
+    HostOperand a1{D.dGn, H, 0, (long long)T * Bt, 0, 0};
+    HostOperand w1{D.w_hh, H, 1, H, 0, 2LL * H};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[1], a1, w1, H, Cfg::BNG));
+  }
+  for (int s = T - 1; s >= 0; --s) {
+    for (int d = 0; d < L->ndir; ++d) {
+      const int t = L->dir[d].reverse ? T - 1 - s : s;
+      b.p[d].seg[0].a_c1 = (int)(t * Bt + L->row0);
+      b.p[d].seg[1].a_c1 = (int)(t * Bt + L->row0);
+      fill_epi(b.p[d].epi, d, s);
+    }
+    IPN_PROPAGATE((launch_umma<Cfg, EpiGruBwd>(b, L->ndir, L->nrows, H, stream)));
+  }
+  return IPN_OK;
+}

@@ -1,0 +1,138 @@
+// LSTM layer forward / backward drivers (AnticipationRNN baseline: uni-directional, zero initial state).
+#include "launch.cuh"
+
+namespace ipn {
+
+template <int W>
+__global__ void lstm_bwd_point_kernel(LstmBwdPoint p, int nrows) {
+  const int chunks = (p.H + W - 1) / W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nrows * chunks) return;
+  const int row = (int)(idx / chunks);
+  const int col0 = (int)(idx % chunks) * W;
+  float dh[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) dh[i] = 0.f;
+  lstm_bwd_pointwise<W>(p, row, col0, min(W, p.H - col0), dh);
+}
+
+static int check_lstm(int core, int act_dt, int T, int B, int H) {
+  IPN_REQUIRE(core == IPN_CORE_SIMT || core == IPN_CORE_UMMA, IPN_ERR_ARG, "lstm: unknown core %d", core);
+  IPN_REQUIRE(core != IPN_CORE_UMMA || act_dt == IPN_BF16, IPN_ERR_ARG, "lstm: the tcgen05 core needs bf16 activations");
+  IPN_REQUIRE(T > 0 && B > 0 && H > 0, IPN_ERR_ARG, "lstm: bad sizes");
+  IPN_REQUIRE(core != IPN_CORE_UMMA || H % 8 == 0, IPN_ERR_ALIGN, "lstm: tcgen05 core needs H %% 8 == 0");
+  return IPN_OK;
+}
+
+}  // namespace ipn
+
+using namespace ipn;
+
+extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "lstm_layer_fwd: null descriptor");
+  IPN_PROPAGATE(ensure_device());
+  IPN_PROPAGATE(check_lstm(L->core, L->act_dt, L->T, L->B, L->H));
+  IPN_REQUIRE(L->w_hh && L->P && L->hseq && L->cseq, IPN_ERR_ARG, "lstm_layer_fwd: null pointer");
+  const int T = L->T, H = L->H, dt = L->act_dt;
+  const long long B = L->B;
+  const long long es = dt == IPN_BF16 ? 2 : 4;
+  auto fill_epi = [&](EpiLstmFwd::Params& e, int s) {
+    e.H = H; e.act_dt = dt; e.trow = s * B;
+    e.P = L->P; e.ldP = L->ldP; e.b_hh = L->b_hh;
+    e.c_prev = L->cseq + s * B * H;
+    e.c_out = L->cseq + (s + 1) * B * H;
+    e.h_out = reinterpret_cast<char*>(L->hseq) + (s + 1) * B * H * es;
+    e.gates = L->gates; e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = L->y_col0;
+  };
+  if (L->core == IPN_CORE_SIMT) {
+    SimtBatch<EpiLstmFwd> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
+    for (int s = 0; s < T; ++s) {
+      SimtProblem<EpiLstmFwd>& P = b.p[0];
+      P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = H; P.in_dt = dt;
+      HostOperand a{L->hseq, H, 0, (T + 1) * B, s * B, 0};
+      HostOperand w{L->w_hh, H, 0, 4LL * H, 0, 0};
+      fill_simt_seg(P.seg[0], a, w, H, dt);
+      fill_epi(P.epi, s);
+      IPN_PROPAGATE(launch_simt<EpiLstmFwd>(b, 1, (int)B, H, stream));
+    }
+    return IPN_OK;
+  }
+  using Cfg = UmmaCfg<4, 64, false, false>;
+  UmmaBatch<EpiLstmFwd> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  UmmaProblem<EpiLstmFwd>& P = b.p[0];
+  P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = H;
+  HostOperand a{L->hseq, H, 0, (T + 1) * B, 0, 0};
+  HostOperand w{L->w_hh, H, 0, 4LL * H, 0, 0};
+  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BNG));
+  for (int s = 0; s < T; ++s) {
+    P.seg[0].a_c1 = (int)(s * B);
+    fill_epi(P.epi, s);
+    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmFwd>(b, 1, (int)B, H, stream)));
+  }
+  return IPN_OK;
+}
+
+extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "lstm_layer_bwd: null descriptor");
+  IPN_PROPAGATE(ensure_device());
+  IPN_PROPAGATE(check_lstm(L->core, L->act_dt, L->T, L->B, L->H));
+  IPN_REQUIRE(L->w_hh && L->hseq && L->cseq && L->gates && L->dP && L->ws, IPN_ERR_ARG, "lstm_layer_bwd: null pointer");
+  const int T = L->T, H = L->H, dt = L->act_dt;
+  const long long B = L->B;
+  auto fill_point = [&](LstmBwdPoint& p, int s) {
+    p.H = H; p.act_dt = dt; p.trow = s * B;
+    p.gates = L->gates;
+    p.c_prev = L->cseq + s * B * H;
+    p.c_cur = L->cseq + (s + 1) * B * H;
+    p.dY = L->dY; p.ld_dy = L->ld_dy; p.y_col0 = L->y_col0;
+    p.dc_in = (s == T - 1) ? nullptr : L->ws + ((s + 1) & 1) * B * H;
+    p.dc_out = L->ws + (s & 1) * B * H;
+    p.dP = L->dP;
+  };
+  {
+    LstmBwdPoint p;
+    fill_point(p, T - 1);
+    constexpr int W = 4;
+    const long long work = B * ((H + W - 1) / W);
+    lstm_bwd_point_kernel<W><<<cdiv(work, 256), 256, 0, stream>>>(p, (int)B);
+    IPN_LAUNCH_CHECK();
+  }
+  if (L->core == IPN_CORE_SIMT) {
+    SimtBatch<EpiLstmBwd> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
+    for (int s = T - 1; s >= 1; --s) {
+      SimtProblem<EpiLstmBwd>& P = b.p[0];
+      P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = 0; P.in_dt = dt;
+      HostOperand a{L->dP, 4LL * H, 0, T * B, s * B, 0};
+      HostOperand w{L->w_hh, H, 1, H, 0, 0};
+      fill_simt_seg(P.seg[0], a, w, 4 * H, dt);
+      P.epi.is_first_step = 0;
+      fill_point(P.epi.pw, s - 1);
+      IPN_PROPAGATE(launch_simt<EpiLstmBwd>(b, 1, (int)B, H, stream));
+    }
+    return IPN_OK;
+  }
+  using Cfg = UmmaCfg<1, 128, false, true>;
+  UmmaBatch<EpiLstmBwd> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  UmmaProblem<EpiLstmBwd>& P = b.p[0];
+  P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = 0;
+  HostOperand a{L->dP, 4LL * H, 0, T * B, 0, 0};
+  HostOperand w{L->w_hh, H, 1, H, 0, 0};
+  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, 4 * H, Cfg::BNG));
+  for (int s = T - 1; s >= 1; --s) {
+    P.seg[0].a_c1 = (int)(s * B);
+    P.epi.is_first_step = 0;
+    fill_point(P.epi.pw, s - 1);
+    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmBwd>(b, 1, (int)B, H, stream)));
+  }
+  return IPN_OK;
+}

@@ -1,0 +1,153 @@
+#include "runtime.h"
+
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+namespace ipn {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int ensure_device() {
+  static std::mutex mu;
+  static int cached[64];
+  static bool init = false;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("no CUDA device available: this library has no CPU fallback");
+    cudaGetLastError();
+    return IPN_ERR_ARCH;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  if (!init) { for (int i = 0; i < 64; ++i) cached[i] = -1; init = true; }
+  if (cached[dev] < 0) {
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cached[dev] = (major == 10) ? 1 : 0;
+    if (!cached[dev]) set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+  }
+  if (!cached[dev]) {
+    set_error("device %d is not sm_100; this library is built for sm_100a only", dev);
+    return IPN_ERR_ARCH;
+  }
+  return IPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptor cache
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+struct TmKey {
+  const void* ptr;
+  unsigned long long inner, outer;
+  long long ld;
+  unsigned box_outer;
+  bool operator==(const TmKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
+  }
+};
+struct TmHash {
+  size_t operator()(const TmKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](unsigned long long v) { h ^= std::hash<unsigned long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix((unsigned long long)k.ld); mix(k.box_outer);
+    return h;
+  }
+};
+
+int get_tensor_map(CUtensorMap* out, const void* ptr, unsigned long long inner, unsigned long long outer,
+                   long long ld, unsigned box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<TmKey, CUtensorMap, TmHash> cache;
+  IPN_REQUIRE(ptr != nullptr, IPN_ERR_ARG, "tensor map: null pointer");
+  IPN_REQUIRE(reinterpret_cast<uintptr_t>(ptr) % 16 == 0, IPN_ERR_ALIGN, "tensor map: pointer %p not 16B aligned", ptr);
+  IPN_REQUIRE(ld % 8 == 0, IPN_ERR_ALIGN, "tensor map: leading dimension %lld not a multiple of 8 bf16", ld);
+  IPN_REQUIRE(inner > 0 && outer > 0 && box_outer > 0 && box_outer <= 256, IPN_ERR_ARG, "tensor map: bad dims");
+  TmKey key{ptr, inner, outer, ld, box_outer};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return IPN_OK; }
+  EncodeTiledFn fn = get_encode_fn();
+  IPN_REQUIRE(fn != nullptr, IPN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IPN_REQUIRE(r == CUDA_SUCCESS, IPN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%lld box=%u",
+              (int)r, ptr, inner, outer, ld, box_outer);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return IPN_OK;
+}
+
+}  // namespace ipn
+
+extern "C" {
+const char* ipn_last_error(void) { return ipn::g_err; }
+int ipn_abi_version(void) { return IPN_ABI_VERSION; }
+int ipn_struct_sizes(int* out_host, int n) {
+  const int sizes[] = {(int)sizeof(IpnRowMap),      (int)sizeof(IpnGemmSeg),  (int)sizeof(IpnGemm),
+                       (int)sizeof(IpnGruDir),      (int)sizeof(IpnGruLayer), (int)sizeof(IpnGruBwdDir),
+                       (int)sizeof(IpnGruLayerBwd), (int)sizeof(IpnLstmLayer), (int)sizeof(IpnLstmLayerBwd),
+                       (int)sizeof(IpnCeKl),        (int)sizeof(IpnPackItem), (int)sizeof(IpnTickDecode)};
+  const int m = (int)(sizeof(sizes) / sizeof(sizes[0]));
+  for (int i = 0; i < n && i < m; ++i) out_host[i] = sizes[i];
+  return m;
+}
+long long ipn_launch_count(void) { return ipn::g_launches.load(); }
+int ipn_device_check(int dev, int* sm_count_host) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || dev >= n) {
+    cudaGetLastError();
+    ipn::set_error("no CUDA device %d (count %d): this library has no CPU fallback", dev, n);
+    return IPN_ERR_ARCH;
+  }
+  int major = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sm_count_host) *sm_count_host = sms;
+  if (major != 10) {
+    ipn::set_error("device %d is not sm_100", dev);
+    return IPN_ERR_ARCH;
+  }
+  return IPN_OK;
+}
+}

@@ -1,0 +1,247 @@
+"""Trainer layer -- same API as the reference's utils/trainer.py (Trainer ABC, train_model,
+loss_and_acc_on_epoch, overridable zero_grad/step) and MeasureVAE/vae_trainer.py, with
+  * the fused CE+KL forward/backward kernel instead of ~10 small torch kernels,
+  * the fused flat Adam instead of the per-tensor optimiser loop,
+  * an NCCL gradient all-reduce over the contiguous gradient arena when torch.distributed is
+    initialised (one process per GPU; the reference has no data parallelism at all),
+  * one device->host sync per step (the loss read the reference also does, utils/trainer.py:154);
+    the NaN / token-range guards are device flags polled with that same sync.
+"""
+import os
+import time
+import datetime
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+from .arena import arena_of
+from .helpers import to_numpy, to_cuda_variable_long
+from .optim import FusedAdam
+
+try:  # progress bars only
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(x):
+        return x
+
+
+class Trainer(ABC):
+    def __init__(self, dataset, model, lr=1e-4, early_stopping=False):
+        self.dataset = dataset
+        self.model = model
+        self.optimizer = FusedAdam(self.model, lr=lr)
+        self.early_stopping = False
+        if early_stopping:
+            self.early_stopping = True
+            self.early_stopper = EarlyStopping()
+        self.check_flags_every = 1
+
+    def train_model(self, batch_size, num_epochs, plot=False, log=False):
+        if log:
+            try:
+                from tensorboard_logger import configure, log_value
+                st = datetime.datetime.fromtimestamp(time.time()).strftime('%Y-%m-%d_%H:%M:%S')
+                configure(os.path.join('runs/' + self.model.__repr__() + st))
+            except ImportError:
+                print("tensorboard_logger not installed: logging disabled")
+                log = False
+        if plot:
+            print("live plotting is not part of the B200 hot path: disabled")
+            plot = False
+        (generator_train, generator_val, _) = self.dataset.data_loaders(batch_size=batch_size, split=(0.70, 0.20))
+        print('Num Train Batches: ', len(generator_train))
+        print('Num Valid Batches: ', len(generator_val))
+        for epoch_index in range(num_epochs):
+            self.update_scheduler(epoch_index)
+            self.model.train()
+            mean_loss_train, mean_accuracy_train = self.loss_and_acc_on_epoch(
+                data_loader=generator_train, epoch_num=epoch_index, train=True)
+            self.model.eval()
+            mean_loss_val, mean_accuracy_val = self.loss_and_acc_on_epoch(
+                data_loader=generator_val, epoch_num=epoch_index, train=False)
+            data_element = {'epoch_index': epoch_index, 'num_epochs': num_epochs, 'mean_loss_train': mean_loss_train,
+                            'mean_accuracy_train': mean_accuracy_train, 'mean_loss_val': mean_loss_val,
+                            'mean_accuracy_val': mean_accuracy_val}
+            if log:
+                log_value('train_loss', mean_loss_train, epoch_index)
+                log_value('train_accu', mean_accuracy_train, epoch_index)
+                log_value('valid_loss', mean_loss_val, epoch_index)
+                log_value('valid_accu', mean_accuracy_val, epoch_index)
+            self.print_epoch_stats(**data_element)
+            if not dist.is_initialized() or dist.get_rank() == 0:
+                self.model.save()
+                if epoch_index > 0 and epoch_index % 10 == 0:
+                    self.model.save_checkpoint(epoch_index)
+            if self.early_stopping:
+                self.early_stopper(mean_loss_val, self.model)
+                if self.early_stopper.early_stop:
+                    print("Early Stopping")
+                    return
+
+    def loss_and_acc_on_epoch(self, data_loader, epoch_num=None, train=True):
+        mean_loss = 0
+        mean_accuracy = 0
+        for sample_id, batch in tqdm(enumerate(data_loader)):
+            batch_data = self.process_batch_data(batch)
+            self.zero_grad()
+            if train:
+                loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
+                loss.backward()
+                self.step()
+            else:
+                with torch.no_grad():
+                    loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
+            mean_loss += to_numpy(loss.mean())        # the one host sync of the step
+            if accuracy is not None:
+                mean_accuracy += to_numpy(accuracy)
+            self.check_device_flags()
+        mean_loss /= len(data_loader)
+        mean_accuracy /= len(data_loader)
+        return (mean_loss, mean_accuracy)
+
+    def check_device_flags(self):
+        """NaN-in-parameters (encoder.py:111-116) and token-range (decoder.py:34-45) guards -> ValueError."""
+        a = arena_of(self.model)
+        flags = torch.stack((a.nan_flag[0], a.range_flag[0])).cpu()
+        if int(flags[0]) != 0:
+            print('Model parameters have become nan')
+            raise ValueError
+        if int(flags[1]) != 0:
+            print("Invalid Values of Indices")
+            raise ValueError
+
+    def zero_grad(self):
+        self.optimizer.zero_grad()
+
+    def step(self):
+        """Gradient all-reduce (sum over ranks, scaled by 1/world inside the Adam kernel) + fused Adam."""
+        scale = 1.0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            a = arena_of(self.model)
+            allreduce_grads(a)
+            scale = 1.0 / dist.get_world_size()
+        self.optimizer.step(grad_scale=scale)
+
+    @abstractmethod
+    def loss_and_acc_for_batch(self, batch, epoch_num=None, train=True):
+        pass
+
+    @abstractmethod
+    def process_batch_data(self, batch):
+        pass
+
+    @abstractmethod
+    def update_scheduler(self, epoch_num):
+        pass
+
+    @staticmethod
+    def print_epoch_stats(epoch_index, num_epochs, mean_loss_train, mean_accuracy_train, mean_loss_val,
+                          mean_accuracy_val):
+        print(f'Train Epoch: {epoch_index + 1}/{num_epochs}')
+        print(f'\tTrain Loss: {mean_loss_train}'
+              f'\tTrain Accuracy: {mean_accuracy_train * 100} %')
+        print(f'\tValid Loss: {mean_loss_val}'
+              f'\tValid Accuracy: {mean_accuracy_val * 100} %')
+
+    @staticmethod
+    def mean_crossentropy_loss(weights, targets):
+        """weights (batch, seq_len, num_notes), targets (batch, seq_len) -> scalar (utils/trainer.py:271-288)"""
+        batch_size, seq_len, num_notes = weights.size()
+        assert (batch_size == targets.size(0))
+        assert (seq_len == targets.size(1))
+        return Fn.fused_ce_kl(weights, targets)[0]
+
+    @staticmethod
+    def mean_accuracy(weights, targets):
+        """utils/trainer.py:290-306 (first maximal index == target)"""
+        with torch.no_grad():
+            return Fn.fused_ce_kl(weights.detach(), targets)[1]
+
+    @staticmethod
+    def mean_crossentropy_loss_alt(weights, targets):
+        """weights (batch, num_measures, seq_len, num_notes) (utils/trainer.py:344-358)"""
+        return Fn.fused_ce_kl(weights, targets)[0]
+
+    @staticmethod
+    def mean_accuracy_alt(weights, targets):
+        with torch.no_grad():
+            return Fn.fused_ce_kl(weights.detach(), targets)[1]
+
+
+def allreduce_grads(arena, bucket_bytes=32 << 20):
+    """Sum-all-reduce of the trainable gradient range in buckets (NCCL over NVLink when the backend is
+    nccl; gloo on CPU for the tests).  The range is contiguous, so buckets are plain slices."""
+    n = arena.n_trainable
+    step = max(1, bucket_bytes // 4)
+    works = []
+    for lo in range(0, n, step):
+        works.append(dist.all_reduce(arena.grad[lo:min(n, lo + step)], op=dist.ReduceOp.SUM, async_op=True))
+    for w in works:
+        w.wait()
+
+
+class VAETrainer(Trainer):
+    """reference: MeasureVAE/vae_trainer.py:10-139"""
+
+    def __init__(self, dataset, model, lr=1e-4):
+        super(VAETrainer, self).__init__(dataset, model, lr)
+
+    def loss_and_acc_for_batch(self, batch, epoch_num=None, train=True):
+        score = batch
+        weights, samples, z_dist, prior_dist, z_tilde, z_prior = self.model(measure_score_tensor=score, train=train)
+        # recons_loss + 0.001 * KL and accuracy in one fused pass (vae_trainer.py:33-39)
+        log_std = getattr(z_dist, "log_std", None)
+        if log_std is None:
+            log_std = z_dist.scale.log()
+        loss, accuracy = Fn.fused_ce_kl(weights, score, z_dist.loc, log_std, beta=0.001)
+        return loss, accuracy
+
+    def process_batch_data(self, batch):
+        score_tensor, _ = batch
+        if hasattr(self.dataset, "n_bars") and score_tensor.dim() == 3:
+            batch_size = score_tensor.size(0)
+            score_tensor = score_tensor.view(batch_size, self.dataset.n_bars, -1)
+            score_tensor = score_tensor.view(batch_size * self.dataset.n_bars, -1)
+        return to_cuda_variable_long(score_tensor)
+
+    def update_scheduler(self, epoch_num):
+        return
+
+    @staticmethod
+    def compute_kld_loss(z_dist, prior_dist, beta=0.001):
+        """vae_trainer.py:128-139, generic torch form (the step loop uses the fused kernel instead)."""
+        kld = torch.distributions.kl.kl_divergence(z_dist, prior_dist)
+        return beta * kld.sum(1).mean()
+
+
+class EarlyStopping:
+    """reference: utils/trainer.py:379-413"""
+
+    def __init__(self, patience=5, verbose=False):
+        self.patience = patience
+        self.verbose = verbose
+        self.counter = 0
+        self.best_score = None
+        self.early_stop = False
+        self.val_loss_min = np.inf
+
+    def __call__(self, val_loss, model):
+        score = -val_loss
+        if self.best_score is None:
+            self.best_score = score
+        elif score <= self.best_score:
+            self.counter += 1
+            if self.counter >= self.patience:
+                self.early_stop = True
+        else:
+            if score - self.best_score < 1e-5:
+                self.counter += 1
+                if self.counter >= self.patience:
+                    self.early_stop = True
+            else:
+                self.best_score = score
+                self.val_loss_min = val_loss
+                self.counter = 0
