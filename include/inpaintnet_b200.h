@@ -67,6 +67,12 @@ int ipn_device_check(int dev, int* sm_count_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long ipn_launch_count(void);
 
+/* Per-kernel-class timing with CUDA events on the launching stream (used by bench.py for the
+ * roofline numbers; off by default).  ipn_prof_report synchronises the device and writes one line per
+ * kernel class: tag \t launches \t total_ms \t algorithmic_flops \t algorithmic_bytes. */
+void ipn_prof_enable(int on);
+int ipn_prof_report(char* buf_host, int cap);
+
 /* 3-level affine row map: off = (r / g1) * s1 + ((r % g1) / g2) * s2 + (r % g2) * s3 (elements) */
 typedef struct {
   int g1, g2;

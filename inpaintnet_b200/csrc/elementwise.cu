@@ -370,6 +370,7 @@ extern "C" {
 
 int ipn_tokens_time_major(const long long* tok64, int B, int T, int V, int* out32, int* range_flag, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("tokens", 0.0, (double)(12.0 * (double)B * T), STREAM);
   IPN_REQUIRE(tok64 && out32 && B > 0 && T > 0, IPN_ERR_ARG, "tokens_time_major: bad args");
   tokens_time_major_kernel<<<cdiv((long long)B * T, 256), 256, 0, STREAM>>>(tok64, B, T, V, out32, range_flag);
   IPN_LAUNCH_CHECK();
@@ -378,6 +379,7 @@ int ipn_tokens_time_major(const long long* tok64, int B, int T, int V, int* out3
 
 int ipn_dec_prev_tokens(const long long* tok64, int B, int V, int* out32, int* range_flag, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("tokens", 0.0, (double)(12.0 * 24.0 * (double)B), STREAM);
   IPN_REQUIRE(tok64 && out32 && B > 0, IPN_ERR_ARG, "dec_prev_tokens: bad args");
   dec_prev_tokens_kernel<<<cdiv((long long)B * 24, 256), 256, 0, STREAM>>>(tok64, B, V, out32, range_flag);
   IPN_LAUNCH_CHECK();
@@ -387,6 +389,7 @@ int ipn_dec_prev_tokens(const long long* tok64, int B, int V, int* out32, int* r
 int ipn_embed_rows(const float* emb, int E, const int* tok, long long rows, void* out, int out_dt, long long ld_out,
                    void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("embed_rows", 0.0, (double)((double)rows * ld_out * (out_dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(emb && tok && out && rows > 0 && ld_out >= E, IPN_ERR_ARG, "embed_rows: bad args");
   embed_rows_kernel<<<cdiv(rows * ld_out, 256), 256, 0, STREAM>>>(emb, E, tok, rows, out, out_dt, ld_out);
   IPN_LAUNCH_CHECK();
@@ -396,6 +399,7 @@ int ipn_embed_rows(const float* emb, int E, const int* tok, long long rows, void
 int ipn_embed_grad(const void* dX, int dx_dt, long long ld_dx, const int* tok, long long rows, int E, int V,
                    float* demb, int skip_id, float* dskip, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("embed_grad", 0.0, (double)((double)rows * E * (dx_dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(dX && tok && demb && rows > 0, IPN_ERR_ARG, "embed_grad: bad args");
   const int smem = (V + 1) * E * (int)sizeof(float);
   IPN_REQUIRE(smem <= 48 * 1024, IPN_ERR_ARG, "embed_grad: table too large for shared memory");
@@ -408,6 +412,7 @@ int ipn_embed_grad(const void* dX, int dx_dt, long long ld_dx, const int* tok, l
 int ipn_argmax_rows(const float* logits, int rows, int V, const IpnRowMap* rowmap, int* tok_out,
                     long long* samples_out, const IpnRowMap* samples_map, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("argmax_rows", 0.0, (double)((double)rows * V * 4.0), STREAM);
   IPN_REQUIRE(logits && rows > 0 && V > 0, IPN_ERR_ARG, "argmax_rows: bad args");
   IpnRowMap z{1, 1, 0, 0, 0};
   argmax_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, STREAM>>>(
@@ -420,6 +425,7 @@ int ipn_argmax_rows(const float* logits, int rows, int V, const IpnRowMap* rowma
 int ipn_rng_keep_mask(unsigned long long seed, unsigned long long offset, long long n, float p_drop, unsigned char* out,
                       void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("rng_keep_mask", 0.0, (double)((double)n), STREAM);
   IPN_REQUIRE(out && n > 0 && p_drop >= 0.f && p_drop < 1.f, IPN_ERR_ARG, "rng_keep_mask: bad args");
   rng_keep_mask_kernel<<<cdiv(cdiv(n, 16), 256), 256, 0, STREAM>>>(seed, offset, n, p_drop, out);
   IPN_LAUNCH_CHECK();
@@ -428,6 +434,7 @@ int ipn_rng_keep_mask(unsigned long long seed, unsigned long long offset, long l
 
 int ipn_rng_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("rng_normal", 0.0, (double)(4.0 * (double)n), STREAM);
   IPN_REQUIRE(out && n > 0, IPN_ERR_ARG, "rng_normal: bad args");
   rng_normal_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, STREAM>>>(seed, offset, n, out);
   IPN_LAUNCH_CHECK();
@@ -454,6 +461,7 @@ int ipn_reparam_bwd(const void* dz, int dz_dt, const float* log_std, const float
 
 int ipn_ce_kl(const IpnCeKl* p, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("ce_kl_fwd_bwd", 0.0, (double)((p ? (double)p->rows * p->V * (4.0 + (p->dlogits ? (p->dl_dt == IPN_BF16 ? 2.0 : 4.0) : 0.0)) + (double)p->rows * 8.0 + (double)p->Bz * p->Z * 16.0 : 0.0)), STREAM);
   IPN_REQUIRE(p && p->weights && p->targets && p->scalars && p->rows > 0 && p->V > 0, IPN_ERR_ARG, "ce_kl: bad args");
   IPN_REQUIRE(!p->dlogits || p->ld_dl >= p->V, IPN_ERR_ARG, "ce_kl: ld_dl < V");
   const int blocks = (int)imin(148 * 8, cdiv(p->rows, 8));
@@ -470,6 +478,7 @@ int ipn_ce_kl(const IpnCeKl* p, void* stream_) {
 int ipn_adam_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float beta1,
                   float beta2, float eps, float grad_scale, int* nan_flag, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("adam_fused", 0.0, (double)(28.0 * (double)n), STREAM);
   IPN_REQUIRE(p && g && m && v && n > 0 && step >= 1, IPN_ERR_ARG, "adam_step: bad args");
   IPN_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, IPN_ERR_ALIGN,
               "adam_step: arenas must be 16B aligned");
@@ -483,6 +492,7 @@ int ipn_adam_step(float* p, const float* g, float* m, float* v, long long n, int
 
 int ipn_pack_bf16(const IpnPackItem* items_dev, int n, int max_rows, int max_ld_dst, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("pack_bf16", 0.0, (double)(0), STREAM);
   IPN_REQUIRE(items_dev && n > 0, IPN_ERR_ARG, "pack_bf16: bad args");
   const long long total = (long long)max_rows * max_ld_dst;
   dim3 grid((unsigned)imin(64, cdiv(total, 256)), n);
@@ -493,6 +503,7 @@ int ipn_pack_bf16(const IpnPackItem* items_dev, int n, int max_rows, int max_ld_
 
 int ipn_colsum(const void* X, int dt, long long ld, long long rows, int cols, float* out, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("colsum", 0.0, (double)((double)rows * cols * (dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(X && out && rows > 0 && cols > 0, IPN_ERR_ARG, "colsum: bad args");
   dim3 grid(cdiv(cols, 64), (unsigned)imin(cdiv(rows, 64), cdiv(2 * 148, cdiv(cols, 64)) + 1));
   colsum_kernel<<<grid, 256, 0, STREAM>>>(X, dt, ld, rows, cols, out);
@@ -503,6 +514,7 @@ int ipn_colsum(const void* X, int dt, long long ld, long long rows, int cols, fl
 int ipn_convert_2d(const void* src, int src_dt, long long ld_src, void* dst, int dst_dt, long long ld_dst,
                    long long rows, int cols, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("convert_2d", 0.0, (double)((double)rows * cols * 6.0), STREAM);
   IPN_REQUIRE(src && dst && rows > 0 && cols > 0, IPN_ERR_ARG, "convert_2d: bad args");
   convert_2d_kernel<<<cdiv(rows * cols, 256), 256, 0, STREAM>>>(src, src_dt, ld_src, dst, dst_dt, ld_dst, rows, cols);
   IPN_LAUNCH_CHECK();
@@ -520,6 +532,7 @@ int ipn_fill_i32(int* dst, long long n, int value, void* stream_) {
 int ipn_sum_slots(const void* X, int dt, long long ld, int slots, long long rows, int cols, void* out, long long ld_out,
                   void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("sum_slots", 0.0, (double)((double)(slots + 1) * rows * cols * (dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(X && out && slots > 0 && rows > 0 && cols > 0, IPN_ERR_ARG, "sum_slots: bad args");
   sum_slots_kernel<<<cdiv(rows * cols, 256), 256, 0, STREAM>>>(X, dt, ld, slots, rows, cols, out, ld_out);
   IPN_LAUNCH_CHECK();
@@ -529,6 +542,7 @@ int ipn_sum_slots(const void* X, int dt, long long ld, int slots, long long rows
 int ipn_dlogits_relayout(const float* dweights, const float* weights, int B, int V, void* out, int out_dt,
                          long long ld_out, void* stream_) {
   IPN_PROPAGATE(ensure_device());
+  ProfScope prof("dlogits_relayout", 0.0, (double)(24.0 * B * (8.0 * V + ld_out * (out_dt == IPN_BF16 ? 2.0 : 4.0))), STREAM);
   IPN_REQUIRE(dweights && weights && out && B > 0 && V > 0 && ld_out >= V, IPN_ERR_ARG, "dlogits_relayout: bad args");
   dlogits_relayout_kernel<<<cdiv(24LL * B * ld_out, 256), 256, 0, STREAM>>>(dweights, weights, B, V, out, out_dt, ld_out);
   IPN_LAUNCH_CHECK();

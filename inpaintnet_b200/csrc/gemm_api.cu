@@ -41,7 +41,7 @@ static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
     IPN_PROPAGATE(fill_umma_seg(P.seg[s], a, bb, sg.K, BNG));
   }
   fill_linear_epi(P.epi, g);
-  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream);
+  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream, TA ? "gemm_umma_tn_wgrad" : (TB ? "gemm_umma_nn_dgrad" : "gemm_umma_nt"));
 }
 
 static int pick_split_k(const IpnGemm* g, int tile_m, int tile_n, int bk) {
@@ -93,7 +93,7 @@ extern "C" int ipn_gemm(const IpnGemm* g, void* stream_) {
       fill_simt_seg(P.seg[s], a, bb, sg.K, g->in_dt);
     }
     fill_linear_epi(P.epi, g);
-    return launch_simt<EpiLinear>(b, 1, g->M, g->N, stream);
+    return launch_simt<EpiLinear>(b, 1, g->M, g->N, stream, "gemm_simt");
   }
 
   IPN_REQUIRE(g->core == IPN_CORE_UMMA, IPN_ERR_ARG, "ipn_gemm: unknown core %d", g->core);

@@ -83,7 +83,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
         HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
         fill_simt_seg(P.seg[0], a, w, H, dt);
       }
-      IPN_PROPAGATE(launch_simt<EpiGruFwd>(b, L->ndir, L->nrows, H, stream));
+      IPN_PROPAGATE(launch_simt<EpiGruFwd>(b, L->ndir, L->nrows, H, stream, "gru_step_fwd_simt"));
     }
     return IPN_OK;
   }
@@ -105,7 +105,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
       const int in_slot = fill_epi(b.p[d].epi, L->dir[d], s);
       b.p[d].seg[0].a_c1 = (int)(in_slot * Bt + L->row0);
     }
-    IPN_PROPAGATE((launch_umma<Cfg, EpiGruFwd>(b, L->ndir, L->nrows, H, stream)));
+    IPN_PROPAGATE((launch_umma<Cfg, EpiGruFwd>(b, L->ndir, L->nrows, H, stream, "gru_step_fwd_umma")));
   }
   return IPN_OK;
 }
@@ -148,6 +148,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     constexpr int W = 4;
     const long long work = (long long)L->nrows * ((H + W - 1) / W);
     dim3 grid(cdiv(work, 256), 1, L->ndir);
+    ProfScope prof("gru_bwd_pointwise", 0.0, 0.0, stream);
     gru_bwd_point_kernel<W><<<grid, 256, 0, stream>>>(p0, p1, L->nrows);
     IPN_LAUNCH_CHECK();
   }
@@ -180,7 +181,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
         fill_simt_seg(P.seg[1], a1, w1, H, dt);
         fill_epi(P.epi, d, s);
       }
-      IPN_PROPAGATE(launch_simt<EpiGruBwd>(b, L->ndir, L->nrows, H, stream));
+      IPN_PROPAGATE(launch_simt<EpiGruBwd>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_simt"));
     }
     return IPN_OK;
   }
@@ -207,7 +208,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
       b.p[d].seg[1].a_c1 = (int)(t * Bt + L->row0);
       fill_epi(b.p[d].epi, d, s);
     }
-    IPN_PROPAGATE((launch_umma<Cfg, EpiGruBwd>(b, L->ndir, L->nrows, H, stream)));
+    IPN_PROPAGATE((launch_umma<Cfg, EpiGruBwd>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));
   }
   return IPN_OK;
 }

@@ -61,8 +61,21 @@ inline int fill_umma_seg(UmmaSeg& s, const HostOperand& a, const HostOperand& b,
   return IPN_OK;
 }
 
+template <class P>
+inline double batch_flops(const P* p, int nprob, int G) {
+  double f = 0;
+  for (int i = 0; i < nprob; ++i) {
+    double k = 0;
+    for (int s = 0; s < p[i].nseg; ++s) k += p[i].seg[s].K;
+    f += 2.0 * p[i].M * (double)p[i].N * G * k;
+  }
+  return f;
+}
+
 template <class Cfg, class Epi>
-int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream) {
+int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
+                const char* tag = "umma") {
+  ProfScope prof(tag, batch_flops(batch.p, nprob, Epi::G), 0.0, stream);
   static bool configured = false;
   auto kern = umma_gemm_kernel<Cfg, Epi>;
   if (!configured) {
@@ -76,7 +89,9 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
 }
 
 template <class Epi>
-int launch_simt(const SimtBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream) {
+int launch_simt(const SimtBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
+                const char* tag = "simt") {
+  ProfScope prof(tag, batch_flops(batch.p, nprob, Epi::G), 0.0, stream);
   dim3 grid(cdiv(maxN, SIMT_BN), cdiv(maxM, SIMT_BM), nprob * batch.split_k);
   simt_gemm_kernel<Epi><<<grid, 256, 0, stream>>>(batch);
   IPN_LAUNCH_CHECK();

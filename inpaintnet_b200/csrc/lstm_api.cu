@@ -56,7 +56,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
       HostOperand w{L->w_hh, H, 0, 4LL * H, 0, 0};
       fill_simt_seg(P.seg[0], a, w, H, dt);
       fill_epi(P.epi, s);
-      IPN_PROPAGATE(launch_simt<EpiLstmFwd>(b, 1, (int)B, H, stream));
+      IPN_PROPAGATE(launch_simt<EpiLstmFwd>(b, 1, (int)B, H, stream, "lstm_step_fwd_simt"));
     }
     return IPN_OK;
   }
@@ -72,7 +72,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   for (int s = 0; s < T; ++s) {
     P.seg[0].a_c1 = (int)(s * B);
     fill_epi(P.epi, s);
-    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmFwd>(b, 1, (int)B, H, stream)));
+    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmFwd>(b, 1, (int)B, H, stream, "lstm_step_fwd_umma")));
   }
   return IPN_OK;
 }
@@ -115,7 +115,7 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
       fill_simt_seg(P.seg[0], a, w, 4 * H, dt);
       P.epi.is_first_step = 0;
       fill_point(P.epi.pw, s - 1);
-      IPN_PROPAGATE(launch_simt<EpiLstmBwd>(b, 1, (int)B, H, stream));
+      IPN_PROPAGATE(launch_simt<EpiLstmBwd>(b, 1, (int)B, H, stream, "lstm_step_bwd_simt"));
     }
     return IPN_OK;
   }
@@ -132,7 +132,7 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
     P.seg[0].a_c1 = (int)(s * B);
     P.epi.is_first_step = 0;
     fill_point(P.epi.pw, s - 1);
-    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmBwd>(b, 1, (int)B, H, stream)));
+    IPN_PROPAGATE((launch_umma<Cfg, EpiLstmBwd>(b, 1, (int)B, H, stream, "lstm_step_bwd_umma")));
   }
   return IPN_OK;
 }

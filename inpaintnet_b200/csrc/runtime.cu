@@ -2,10 +2,13 @@
 
 #include <stdarg.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <map>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 namespace ipn {
 
@@ -45,6 +48,44 @@ int ensure_device() {
     return IPN_ERR_ARCH;
   }
   return IPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel-class event timing
+// ---------------------------------------------------------------------------------------------
+struct ProfRec {
+  const char* tag;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void prof_begin(const char* tag, double flops, double bytes, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{tag, flops, bytes, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, stream);
+  g_prof.push_back(r);
+}
+
+void prof_end(cudaStream_t stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -133,6 +174,44 @@ int ipn_struct_sizes(int* out_host, int n) {
   return m;
 }
 long long ipn_launch_count(void) { return ipn::g_launches.load(); }
+
+void ipn_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(ipn::g_prof_mu);
+  ipn::g_prof_on = on != 0;
+}
+
+// Synchronises the device, aggregates the recorded launches per tag and writes lines
+//   tag<TAB>launches<TAB>total_ms<TAB>flops<TAB>bytes
+// into buf (NUL terminated, truncated to cap). Clears the records. Returns the number of tags.
+int ipn_prof_report(char* buf_host, int cap) {
+  using namespace ipn;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    Agg& a = agg[r.tag];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  std::string out;
+  char line[512];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.6e\t%.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+             kv.second.flops, kv.second.bytes);
+    out += line;
+  }
+  if (buf_host && cap > 0) {
+    const int n = (int)std::min<size_t>(out.size(), (size_t)cap - 1);
+    memcpy(buf_host, out.data(), n);
+    buf_host[n] = 0;
+  }
+  return (int)agg.size();
+}
 int ipn_device_check(int dev, int* sm_count_host) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || dev >= n) {

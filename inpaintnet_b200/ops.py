@@ -222,3 +222,18 @@ def convert_2d(src, src_dt, ld_src, dst, dst_dt, ld_dst, rows, cols):
 
 def launch_count():
     return lib().ipn_launch_count()
+
+
+def prof_enable(on):
+    lib().ipn_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    """-> {tag: dict(launches, ms, flops, bytes)}; synchronises the device and clears the records."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().ipn_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        tag, n, ms, fl, by = line.split("\t")
+        out[tag] = dict(launches=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out
