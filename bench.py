@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=256, help="measures per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--inpaint-queries", type=int, default=8192, help="inpainting queries per GPU (0 = skip)")
     return ap.parse_args()
 
 
@@ -169,6 +170,39 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def run_inpaint(args, world, rank, timed):
+    from inpaintnet_b200.measure_vae import MeasureVAE
+    from inpaintnet_b200.latent_rnn import LatentRNN
+    from inpaintnet_b200.data import SyntheticFolkDataset
+    Q = args.inpaint_queries
+    ds = SyntheticFolkDataset(num_notes=V)
+    torch.manual_seed(0)
+    vae = MeasureVAE(ds)
+    model = LatentRNN(ds, vae, 2, 512, 0.5, torch.nn.GRU, auto_reg=False)
+    model.cuda()
+    model.set_precision(args.precision)
+    model.eval()
+    g = torch.Generator().manual_seed(99 + rank)
+    host = torch.randint(0, V, (Q, 16, 24), generator=g, dtype=torch.int32).pin_memory()
+    n_p, n_t, n_f = 6, 4, 6   # script_gen_diff_models.py:144-146
+
+    def query(_i):
+        score = host.cuda(non_blocking=True).long()
+        past, target, future = score[:, :n_p], score[:, n_p:n_p + n_t], score[:, n_p + n_t:]
+        with torch.no_grad():
+            w, s, z = model(past, future, target, n_t, train=False)
+        return s.cpu()   # the decoded tokens come back to the host
+
+    for i in range(2):
+        query(i)
+    reps = 5
+    ms = timed(query, reps)
+    return {"metric": "inpaint_queries_per_sec", "value": world * Q * reps / (ms / 1e3), "unit": "queries/s",
+            "queries_per_gpu": Q, "split": "6/4/6", "ms_per_batch": ms / reps, "end_to_end": True,
+            "note": "host int32 tokens -> H2D -> encode 12 context measures + LatentRNN + argmax decode of 4 gap "
+                    "measures -> D2H tokens; target-encode (unused by the non-autoregressive model) skipped"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -268,6 +302,12 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- second half of BASELINE.json's metric: batched inpainting inference (configs[3]): encode the 12
+    # context measures, LatentRNN generates 4 gap latents, argmax decode; queries sharded over ranks.
+    inpaint = None
+    if args.inpaint_queries > 0:
+        inpaint = run_inpaint(args, world, rank, timed)
+
     if rank == 0:
         peaks = {}
         src = "measured (MEASURED_PEAKS.json, sustained bf16 / HBM copy)"
@@ -322,6 +362,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernels": breakdown,
+            "inpaint": inpaint,
         }
         print(json.dumps(line))
     if world > 1:

@@ -152,6 +152,9 @@ typedef struct {
   int reverse;
   int y_col0;
   int final_col0;
+  void* final_out_dir; /* when non-null: this direction writes its final state here instead of IpnGruLayer.final_out */
+  int final_dir_dt;
+  long long ld_final_dir;
 } IpnGruDir;
 
 typedef struct {
@@ -278,6 +281,9 @@ int ipn_sum_slots(const void* X, int dt, long long ld, int slots, long long rows
  * [(j*4B + i*B + b), ld_out] (t = 6i+j), ReLU mask (weights > 0) applied, zero padded, act dtype. */
 int ipn_dlogits_relayout(const float* dweights, const float* weights, int B, int V, void* out, int out_dt,
                          long long ld_out, void* stream);
+/* same with the (b, t) element of the source tensors at  map(b) + t*V  instead of (b*24 + t)*V */
+int ipn_dlogits_relayout_mapped(const float* dweights, const float* weights, int B, int V, const IpnRowMap* map,
+                                void* out, int out_dt, long long ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tick decoder, argmax-feedback mode: the 24 serial ticks of MeasureVAE/decoder.py:473-529 when
@@ -304,6 +310,9 @@ typedef struct {
   float* weights;     /* (B, 24, V) fp32 */
   long long* samples; /* (B, 1, 24) int64 */
   int* tokprev;       /* [24B] int32, decoder order */
+  int use_maps;       /* 0: row b of tick t -> weights + (b*24 + t)*V, samples + b*24 + t */
+  IpnRowMap wmap;     /* else: weights + wmap(b) + t*V   and   samples + smap(b) + t */
+  IpnRowMap smap;
 } IpnTickDecode;
 int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream);
 
@@ -378,6 +387,9 @@ int ipn_pack_bf16(const IpnPackItem* items_dev, int n, int max_rows, int max_ld_
 
 /* out[n] += sum_r X[r, n]  (bias gradients) */
 int ipn_colsum(const void* X, int dt, long long ld, long long rows, int cols, float* out, void* stream);
+/* same, and additionally out2[n] += the same sums for n < cols2 (b_hh shares its r,z part with b_ih) */
+int ipn_colsum2(const void* X, int dt, long long ld, long long rows, int cols, float* out, float* out2, int cols2,
+                void* stream);
 /* dst[i] = (dt) src[i]; generic dtype conversion, 2-D with leading dims */
 int ipn_convert_2d(const void* src, int src_dt, long long ld_src, void* dst, int dst_dt, long long ld_dst,
                    long long rows, int cols, void* stream);

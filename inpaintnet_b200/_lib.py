@@ -34,7 +34,7 @@ class Gemm(C.Structure):
 class GruDir(C.Structure):
     _fields_ = [("w_hh", vp), ("b_hh", vp), ("P", vp), ("ldP", ll), ("P_bcast", i32), ("table", vp),
                 ("ld_table", ll), ("tok", vp), ("pvec", vp), ("hseq", vp), ("gates", vp), ("reverse", i32),
-                ("y_col0", i32), ("final_col0", i32)]
+                ("y_col0", i32), ("final_col0", i32), ("final_out_dir", vp), ("final_dir_dt", i32), ("ld_final_dir", ll)]
 
 
 class GruLayer(C.Structure):
@@ -80,7 +80,8 @@ class PackItem(C.Structure):
 class TickDecode(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("B", i32), ("H", i32), ("V", i32), ("l0", GruDir), ("l1", GruDir),
                 ("yt0", vp), ("yt1", vp), ("mask", vp), ("mask_scale", f32), ("w_ih1", vp), ("b_ih1", vp),
-                ("Pt1", vp), ("w_v", vp), ("b_v", vp), ("weights", vp), ("samples", vp), ("tokprev", vp)]
+                ("Pt1", vp), ("w_v", vp), ("b_v", vp), ("weights", vp), ("samples", vp), ("tokprev", vp),
+                ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap)]
 
 
 STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
@@ -108,6 +109,7 @@ SYMBOLS = {
     "ipn_fill_i32": (i32, [vp, ll, i32, vp]),
     "ipn_sum_slots": (i32, [vp, i32, ll, i32, ll, i32, vp, ll, vp]),
     "ipn_dlogits_relayout": (i32, [vp, vp, i32, i32, vp, i32, ll, vp]),
+    "ipn_dlogits_relayout_mapped": (i32, [vp, vp, i32, i32, C.POINTER(RowMap), vp, i32, ll, vp]),
     "ipn_tick_decode_argmax": (i32, [C.POINTER(TickDecode), vp]),
     "ipn_rng_keep_mask": (i32, [C.c_ulonglong, C.c_ulonglong, ll, f32, vp, vp]),
     "ipn_rng_normal": (i32, [C.c_ulonglong, C.c_ulonglong, ll, vp, vp]),
@@ -117,6 +119,7 @@ SYMBOLS = {
     "ipn_adam_step": (i32, [vp, vp, vp, vp, ll, i32, f32, f32, f32, f32, f32, vp, vp]),
     "ipn_pack_bf16": (i32, [vp, i32, i32, i32, vp]),
     "ipn_colsum": (i32, [vp, i32, ll, ll, i32, vp, vp]),
+    "ipn_colsum2": (i32, [vp, i32, ll, ll, i32, vp, vp, i32, vp]),
     "ipn_convert_2d": (i32, [vp, i32, ll, vp, i32, ll, ll, i32, vp]),
 }
 

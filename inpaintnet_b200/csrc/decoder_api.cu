@@ -35,6 +35,9 @@ extern "C" int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream) {
 
   IpnRowMap wmap{1 << 30, 1 << 30, 0, 0, 24LL * V};  // row b -> b*24V
   IpnRowMap smap{1 << 30, 1 << 30, 0, 0, 24};        // row b -> b*24
+  if (p->use_maps) { wmap = p->wmap; smap = p->smap; }
+  gv.use_rowmap = 1;
+  gv.rowmap = wmap;
 
   for (int t = 0; t < 24; ++t) {
     const int i = t / 6, j = t % 6;

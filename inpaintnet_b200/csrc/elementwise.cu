@@ -301,19 +301,40 @@ __global__ void pack_bf16_kernel(const IpnPackItem* items) {
   }
 }
 
-__global__ void colsum_kernel(const void* X, int dt, long long ld, long long rows, int cols, float* out) {
-  // block: 64 columns x 4 row lanes; each block reduces a chunk of rows
-  __shared__ float sm[4][64];
-  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cx;
+// column sums: block = 16 column-groups of 8 columns x 16 row lanes; 16-byte loads when aligned
+__global__ void colsum_kernel(const void* X, int dt, long long ld, long long rows, int cols, float* out, float* out2,
+                              int cols2) {
+  __shared__ float sm[16][129];
+  const int cg = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 128 + cg * 8;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  float acc = 0.f;
-  if (c < cols)
-    for (long long r = r0 + ry; r < r1; r += 4) acc += ld_act(X, r * ld + c, dt);
-  sm[ry][cx] = acc;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (c0 < cols) {
+    const int nvalid = min(8, cols - c0);
+    const bool vec = vec_ok(X, ld, dt) && nvalid == 8;
+    for (long long r = r0 + ry; r < r1; r += 16) {
+      float v[8];
+      ld_act_n<8>(X, r * ld + c0, dt, vec, nvalid, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[ry][cg * 8 + k] = acc[k];
   __syncthreads();
-  if (ry == 0 && c < cols) atomicAdd(&out[c], sm[0][cx] + sm[1][cx] + sm[2][cx] + sm[3][cx]);
+  if (threadIdx.x < 128) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t += sm[i][threadIdx.x];
+      atomicAdd(&out[c], t);
+      if (out2 != nullptr && c < cols2) atomicAdd(&out2[c], t);
+    }
+  }
 }
 
 __global__ void convert_2d_kernel(const void* src, int sdt, long long lds, void* dst, int ddt, long long ldd,
@@ -343,7 +364,7 @@ __global__ void sum_slots_kernel(const void* X, int dt, long long ld, int slots,
 }
 
 __global__ void dlogits_relayout_kernel(const float* dw, const float* w, int B, int V, void* out, int out_dt,
-                                        long long ld_out) {
+                                        long long ld_out, IpnRowMap map, int use_map) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (row_out, c)
   if (i >= 24LL * B * ld_out) return;
   const long long ro = i / ld_out;
@@ -354,7 +375,7 @@ __global__ void dlogits_relayout_kernel(const float* dw, const float* w, int B, 
   const int t = 6 * ib + j;
   float g = 0.f;
   if (c < V) {
-    const long long src = ((long long)b * 24 + t) * V + c;
+    const long long src = (use_map ? map_row(map, b) : (long long)b * 24 * V) + (long long)t * V + c;
     g = (w[src] > 0.f) ? dw[src] : 0.f;
   }
   st_act(out, i, g, out_dt);
@@ -501,14 +522,21 @@ int ipn_pack_bf16(const IpnPackItem* items_dev, int n, int max_rows, int max_ld_
   return IPN_OK;
 }
 
-int ipn_colsum(const void* X, int dt, long long ld, long long rows, int cols, float* out, void* stream_) {
+int ipn_colsum2(const void* X, int dt, long long ld, long long rows, int cols, float* out, float* out2, int cols2,
+                void* stream_) {
   IPN_PROPAGATE(ensure_device());
   ProfScope prof("colsum", 0.0, (double)((double)rows * cols * (dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(X && out && rows > 0 && cols > 0, IPN_ERR_ARG, "colsum: bad args");
-  dim3 grid(cdiv(cols, 64), (unsigned)imin(cdiv(rows, 64), cdiv(2 * 148, cdiv(cols, 64)) + 1));
-  colsum_kernel<<<grid, 256, 0, STREAM>>>(X, dt, ld, rows, cols, out);
+  const int gx = cdiv(cols, 128);
+  const long long want = cdiv(8 * 148, gx);
+  dim3 grid(gx, (unsigned)imin(cdiv(rows, 64), want < 1 ? 1 : want));
+  colsum_kernel<<<grid, 256, 0, STREAM>>>(X, dt, ld, rows, cols, out, out2, cols2);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
+}
+
+int ipn_colsum(const void* X, int dt, long long ld, long long rows, int cols, float* out, void* stream_) {
+  return ipn_colsum2(X, dt, ld, rows, cols, out, nullptr, 0, stream_);
 }
 
 int ipn_convert_2d(const void* src, int src_dt, long long ld_src, void* dst, int dst_dt, long long ld_dst,
@@ -544,7 +572,17 @@ int ipn_dlogits_relayout(const float* dweights, const float* weights, int B, int
   IPN_PROPAGATE(ensure_device());
   ProfScope prof("dlogits_relayout", 0.0, (double)(24.0 * B * (8.0 * V + ld_out * (out_dt == IPN_BF16 ? 2.0 : 4.0))), STREAM);
   IPN_REQUIRE(dweights && weights && out && B > 0 && V > 0 && ld_out >= V, IPN_ERR_ARG, "dlogits_relayout: bad args");
-  dlogits_relayout_kernel<<<cdiv(24LL * B * ld_out, 256), 256, 0, STREAM>>>(dweights, weights, B, V, out, out_dt, ld_out);
+  IpnRowMap z{1, 1, 0, 0, 0};
+  dlogits_relayout_kernel<<<cdiv(24LL * B * ld_out, 256), 256, 0, STREAM>>>(dweights, weights, B, V, out, out_dt, ld_out, z, 0);
+  IPN_LAUNCH_CHECK();
+  return IPN_OK;
+}
+
+int ipn_dlogits_relayout_mapped(const float* dweights, const float* weights, int B, int V, const IpnRowMap* map,
+                                void* out, int out_dt, long long ld_out, void* stream_) {
+  IPN_PROPAGATE(ensure_device());
+  IPN_REQUIRE(dweights && weights && out && map && B > 0 && V > 0 && ld_out >= V, IPN_ERR_ARG, "dlogits_relayout: bad args");
+  dlogits_relayout_kernel<<<cdiv(24LL * B * ld_out, 256), 256, 0, STREAM>>>(dweights, weights, B, V, out, out_dt, ld_out, *map, 1);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }

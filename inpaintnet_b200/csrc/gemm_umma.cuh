@@ -14,6 +14,7 @@ namespace ipn {
 
 constexpr int UMMA_BM = 128;
 constexpr int UMMA_BK = 64;  // bf16 elements per stage along K (= 128 bytes, one swizzle row)
+constexpr int UMMA_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 warps per TMEM lane quadrant)
 
 struct UmmaSeg {
   alignas(64) CUtensorMap tmA;
@@ -48,9 +49,11 @@ struct UmmaCfg {
   static constexpr int A_BYTES = UMMA_BM * UMMA_BK * 2;
   static constexpr int B_BYTES = BN * UMMA_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int MAX_SMEM = 227 * 1024 - 2048;
+  // Two CTAs per SM: one CTA's epilogue (global-memory latency bound) overlaps the other's mainloop and
+  // the memory-level parallelism per SM doubles.  ~110 KB of stages per CTA, at least 2 stages.
+  static constexpr int MAX_SMEM = 110 * 1024;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256] for M=128");
@@ -59,7 +62,7 @@ struct UmmaCfg {
 };
 
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
+__global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   static_assert(Epi::G == Cfg::G, "epilogue / tile gate count mismatch");
   constexpr int G = Cfg::G, BNG = Cfg::BNG, BN = Cfg::BN, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -171,15 +174,16 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       ptx::umma_commit(tmem_full_bar);
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 16-column chunks
     const int row = m0 + q * 32 + lane;
     if (nchunks > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
 #pragma unroll 1
-    for (int c = 0; c < BNG / 16; ++c) {
+    for (int c = half; c < BNG / 16; c += 2) {
       const int col0 = n0 + c * 16;
       if (col0 >= P.N) break;  // warp uniform
       float acc[G][16];

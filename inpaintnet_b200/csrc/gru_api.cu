@@ -64,8 +64,14 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = D.y_col0; e.mask = L->mask; e.ld_mask = L->ld_mask;
     e.mask_scale = L->mask_scale;
     const bool last = (s == T - 1);
-    e.final_out = last ? L->final_out : nullptr;
-    e.final_dt = L->final_dt; e.ld_final = L->ld_final; e.final_col0 = D.final_col0;
+    if (D.final_out_dir != nullptr) {
+      e.final_out = last ? D.final_out_dir : nullptr;
+      e.final_dt = D.final_dir_dt; e.ld_final = D.ld_final_dir;
+    } else {
+      e.final_out = last ? L->final_out : nullptr;
+      e.final_dt = L->final_dt; e.ld_final = L->ld_final;
+    }
+    e.final_col0 = D.final_col0;
     return in_slot;
   };
 

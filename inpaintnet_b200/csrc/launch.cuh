@@ -83,7 +83,7 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
     configured = true;
   }
   dim3 grid(cdiv(maxN, Cfg::BNG), cdiv(maxM, UMMA_BM), nprob * batch.split_k);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(batch);
+  kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(batch);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }

@@ -76,8 +76,9 @@ def gemm(core, in_dt, M, N, segs, out, out_dt, ld_out, bias=0, act=ACT_NONE, alp
 
 
 def gru_dir(w_hh, b_hh, hseq, gates=0, P=0, ldP=0, P_bcast=0, table=0, ld_table=0, tok=0, pvec=0, reverse=0,
-            y_col0=0, final_col0=0):
+            y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0):
     d = L.GruDir()
+    d.final_out_dir, d.final_dir_dt, d.ld_final_dir = final_out or None, final_dt, ld_final
     d.w_hh, d.b_hh, d.P, d.ldP, d.P_bcast = w_hh, b_hh, P or None, ldP, P_bcast
     d.table, d.ld_table, d.tok, d.pvec = table or None, ld_table, tok or None, pvec or None
     d.hseq, d.gates, d.reverse, d.y_col0, d.final_col0 = hseq, gates or None, reverse, y_col0, final_col0
@@ -134,8 +135,12 @@ def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP
 
 
 def tick_decode_argmax(prec, B, H, V, l0, l1, yt0, yt1, mask, mask_scale, w_ih1, b_ih1, Pt1, w_v, b_v, weights,
-                       samples, tokprev):
+                       samples, tokprev, wmap=None, smap=None):
     p = L.TickDecode()
+    if wmap is not None:
+        p.use_maps = 1
+        p.wmap.g1, p.wmap.g2, p.wmap.s1, p.wmap.s2, p.wmap.s3 = wmap
+        p.smap.g1, p.smap.g2, p.smap.s1, p.smap.s2, p.smap.s3 = smap
     p.core, p.act_dt, p.B, p.H, p.V = prec.core, prec.act, B, H, V
     p.l0, p.l1 = l0, l1
     p.yt0, p.yt1, p.mask, p.mask_scale = yt0, yt1, mask or None, mask_scale
@@ -168,8 +173,12 @@ def sum_slots(X, dt, ld, slots, rows, cols, out, ld_out):
     L.check(lib().ipn_sum_slots(X, dt, ld, slots, rows, cols, out, ld_out, stream()))
 
 
-def dlogits_relayout(dweights, weights, B, V, out, out_dt, ld_out):
-    L.check(lib().ipn_dlogits_relayout(dweights, weights, B, V, out, out_dt, ld_out, stream()))
+def dlogits_relayout(dweights, weights, B, V, out, out_dt, ld_out, bmap=None):
+    if bmap is None:
+        L.check(lib().ipn_dlogits_relayout(dweights, weights, B, V, out, out_dt, ld_out, stream()))
+    else:
+        m = L.RowMap(*bmap)
+        L.check(lib().ipn_dlogits_relayout_mapped(dweights, weights, B, V, C.byref(m), out, out_dt, ld_out, stream()))
 
 
 def rng_keep_mask(seed, offset, n, p_drop, out):
@@ -212,8 +221,8 @@ def pack_bf16(items_dev, n, max_rows, max_ld):
     L.check(lib().ipn_pack_bf16(items_dev, n, max_rows, max_ld, stream()))
 
 
-def colsum(X, dt, ld, rows, cols, out):
-    L.check(lib().ipn_colsum(X, dt, ld, rows, cols, out, stream()))
+def colsum(X, dt, ld, rows, cols, out, out2=0, cols2=0):
+    L.check(lib().ipn_colsum2(X, dt, ld, rows, cols, out, out2 or None, cols2, stream()))
 
 
 def convert_2d(src, src_dt, ld_src, dst, dst_dt, ld_dst, rows, cols):

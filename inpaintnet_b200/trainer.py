@@ -217,6 +217,73 @@ class VAETrainer(Trainer):
         return beta * kld.sum(1).mean()
 
 
+class LatentRNNTrainer(Trainer):
+    """reference: LatentRNN/latent_rnn_trainer.py:8-176"""
+
+    def __init__(self, dataset, model, lr=1e-4, early_stopping=False):
+        super(LatentRNNTrainer, self).__init__(dataset, model, lr, early_stopping)
+        self.min_num_measures_target = 2
+        self.max_num_measure_target = 6
+        assert (self.max_num_measure_target >= self.min_num_measures_target)
+        assert (self.dataset.n_bars > self.min_num_measures_target)
+        assert (self.dataset.n_bars > self.max_num_measure_target)
+        self.measure_seq_len = self.dataset.subdivision * self.dataset.num_beats_per_bar
+
+    def process_batch_data(self, batch):
+        score_tensor, _ = batch
+        return self.split_score_stochastic(score_tensor)
+
+    def loss_and_acc_for_batch(self, batch, epoch_num=None, train=True):
+        tensor_past, tensor_future, tensor_target = batch
+        num_measures_past = tensor_past.size(1)
+        num_measures_future = tensor_future.size(1)
+        weights, pred, _ = self.model(past_context=tensor_past, future_context=tensor_future, target=tensor_target,
+                                      measures_to_generate=self.dataset.n_bars - num_measures_past - num_measures_future,
+                                      train=train)
+        loss, accuracy = Fn.fused_ce_kl(weights, tensor_target)   # latent_rnn_trainer.py:58-66 in one pass
+        return loss, accuracy
+
+    def update_scheduler(self, epoch_num):
+        return
+
+    def split_score_stochastic(self, score_tensor, extra_outs=False, fix_num_target=None):
+        """latent_rnn_trainer.py:77-132.  The split is drawn with torch.randint on the host: under data
+        parallelism all ranks must share the torch seed so shapes (and therefore kernels) agree."""
+        measures_tensor = LatentRNNTrainer.split_to_measures(score_tensor, self.measure_seq_len)
+        num_measures = measures_tensor.size(1)
+        assert (num_measures == self.dataset.n_bars)
+        if fix_num_target is None:
+            num_target = int(torch.randint(low=self.min_num_measures_target, high=self.max_num_measure_target + 1,
+                                           size=(1,)).item())
+        else:
+            num_target = fix_num_target
+        num_past = int(torch.randint(low=1, high=num_measures - num_target - 1, size=(1,)).item())
+        num_future = num_measures - num_past - num_target
+        tensor_past, tensor_future, tensor_target = LatentRNNTrainer.split_score(
+            score_tensor=score_tensor, num_past=num_past, num_future=num_future, num_target=num_target,
+            measure_seq_len=self.measure_seq_len)
+        if extra_outs:
+            return tensor_past, tensor_future, tensor_target, num_past, num_target
+        return tensor_past, tensor_future, tensor_target
+
+    @staticmethod
+    def split_score(score_tensor, num_past, num_future, num_target, measure_seq_len):
+        measures_tensor = LatentRNNTrainer.split_to_measures(score_tensor, measure_seq_len)
+        num_measures = measures_tensor.size(1)
+        assert (num_measures == num_past + num_future + num_target)
+        tensor_past = to_cuda_variable_long(measures_tensor[:, 0:num_past, :])
+        tensor_future = to_cuda_variable_long(measures_tensor[:, num_measures - num_future:, :])
+        tensor_target = to_cuda_variable_long(measures_tensor[:, num_past:num_measures - num_future, :])
+        return tensor_past, tensor_future, tensor_target
+
+    @staticmethod
+    def split_to_measures(score_tensor, measure_seq_len):
+        batch_size, _, seq_len = score_tensor.size()
+        if seq_len % measure_seq_len != 0:
+            raise ValueError
+        return score_tensor.reshape(batch_size, -1, measure_seq_len)
+
+
 class EarlyStopping:
     """reference: utils/trainer.py:379-413"""
 

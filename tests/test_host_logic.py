@@ -95,3 +95,34 @@ def test_plumbing_dry_run(prec, tf):
     assert w.shape == (1, B, 24, V) and s.shape == (1, 1, B * 24)
     for n, p in m.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape, n
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_latent_rnn_plumbing_dry_run(prec):
+    if torch.cuda.is_available():
+        pytest.skip("dry run is a CPU-only plumbing check")
+    from inpaintnet_b200.latent_rnn import LatentRNN
+    from inpaintnet_b200.trainer import LatentRNNTrainer
+    V, H, Z, B = 20, 32, 16, 3
+    ds = SyntheticFolkDataset(num_notes=V)
+    vae = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
+    m = LatentRNN(ds, vae, 2, 32, 0.5, torch.nn.GRU, auto_reg=False).set_precision(prec)
+    sd = m.state_dict()
+    assert len(sd) == 103 and "x_0" in sd and "vae_model.decoder.x_0" in sd
+    tr = LatentRNNTrainer(ds, m)
+    score = torch.randint(0, V, (B, 1, 384), dtype=torch.int32)
+    with stubbed():
+        m.train()
+        batch = tr.process_batch_data((score, None))
+        tr.zero_grad()
+        loss, acc = tr.loss_and_acc_for_batch(batch, 0, train=True)
+        loss.backward()
+        tr.step()
+    n_t = batch[2].shape[1]
+    for n, p in m.named_parameters():
+        if n.startswith("vae_model."):
+            assert not p.requires_grad
+        else:
+            assert p.grad is not None, n
+    a = arena_of(m)
+    assert a.n_trainable < a.total and a.names[0] == "x_0"
