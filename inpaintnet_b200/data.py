@@ -68,7 +68,8 @@ class SyntheticFolkDataset:
         va = torch.utils.data.Subset(ds, range(a, b))
         te = torch.utils.data.Subset(ds, range(b, n))
         pin = torch.cuda.is_available()
-        mk = lambda d, shuffle: DataLoader(d, batch_size=batch_size, shuffle=shuffle, pin_memory=pin, drop_last=True)
+        mk = lambda d, shuffle: DataLoader(d, batch_size=batch_size, shuffle=shuffle and len(d) > 0, pin_memory=pin,
+                                       drop_last=True)
         return mk(tr, True), mk(va, False), mk(te, False)
 
 

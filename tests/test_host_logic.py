@@ -126,3 +126,46 @@ def test_latent_rnn_plumbing_dry_run(prec):
             assert p.grad is not None, n
     a = arena_of(m)
     assert a.n_trainable < a.total and a.names[0] == "x_0"
+
+
+def test_reference_train_script_runs_unchanged_against_dropin():
+    """The reference's own train_measure_vae.py, unmodified, imported with inpaintnet_b200/dropin first on
+    sys.path (stub library: plumbing only).  Needs /root/reference, so it runs in the build container."""
+    import importlib.util
+    import sys
+    ref = "/root/reference/train_measure_vae.py"
+    if not os.path.exists(ref) or torch.cuda.is_available():
+        pytest.skip("reference tree not mounted (or GPU box)")
+    dropin = os.path.join(ROOT, "inpaintnet_b200", "dropin")
+    tops = ("MeasureVAE", "LatentRNN", "utils", "DatasetManager", "AnticipationRNN")
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k.split(".")[0] in tops}
+    for m in saved_mods:
+        del sys.modules[m]
+    sys.path.insert(0, dropin)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_train_measure_vae", ref)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        import inpaintnet_b200.data as D
+        orig = D.SyntheticFolkDataset.__init__
+
+        def small(self, *a, **k):
+            k["num_sequences"] = 8
+            k.setdefault("num_notes", 20)
+            orig(self, *a, **k)
+
+        D.SyntheticFolkDataset.__init__ = small
+        try:
+            with stubbed():
+                mod.main.callback(note_embedding_dim=10, metadata_embedding_dim=2, num_encoder_layers=2,
+                                  encoder_hidden_size=32, encoder_dropout_prob=0.5, has_metadata=False,
+                                  latent_space_dim=16, num_decoder_layers=2, decoder_hidden_size=32,
+                                  decoder_dropout_prob=0.5, batch_size=2, num_epochs=1, train=True, plot=False,
+                                  log=False, lr=1e-4)
+        finally:
+            D.SyntheticFolkDataset.__init__ = orig
+    finally:
+        sys.path[:] = saved_path
+        for m in [k for k in sys.modules if k.split(".")[0] in tops]:
+            del sys.modules[m]
+        sys.modules.update(saved_mods)
