@@ -1,5 +1,13 @@
-// Epilogue functors shared by the tcgen05 core (W = 16 columns per call, thread == output row)
-// and the fp32 SIMT core (W = 4).  acc[g][i] is the accumulator of gate g, column col0 + i.
+// Epilogue functors shared by the tcgen05 core and the fp32 SIMT core.
+//
+// "Lanes = output columns": both cores hand a functor ONE output column `col` and W consecutive output
+// rows row0..row0+W-1 (acc[g][i] = accumulator of gate g at (row0+i, col)).  In the tcgen05 core a TMEM
+// lane is an output column, so the 32 lanes of a warp touch 32 CONSECUTIVE columns of the same row:
+// every global access of the epilogue is a coalesced 64-byte (bf16) or 128-byte (fp32) segment, with no
+// shared-memory staging, for any number of input/output arrays.  Per-column constants (biases, constant
+// input projection) are loaded once per thread in col_init().
+//
+// Each functor first issues all loads of its W rows (memory-level parallelism), then computes and stores.
 #pragma once
 #include "common.cuh"
 
@@ -28,51 +36,58 @@ struct EpiLinear {
     float mul_scale;
     int accumulate;
   };
-
-  template <int W>
-  static __device__ __forceinline__ void apply(const Params& p, int row, int col0, int nvalid, float (&acc)[1][W]) {
-    float v[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      float x = acc[0][i];
-      if (p.bias != nullptr && i < nvalid) x += p.bias[col0 + i];
-      v[i] = apply_act(x, p.act) * p.alpha;
+  struct Col {
+    float bias;
+    char* base;  // output base pointer after the column split
+    int c;       // column inside the split block
+  };
+  static __device__ __forceinline__ void col_init(const Params& p, int col, Col& cc) {
+    cc.bias = p.bias != nullptr ? p.bias[col] : 0.f;
+    cc.base = reinterpret_cast<char*>(p.out);
+    cc.c = col;
+    if (p.split_cols > 0) {
+      const int q = col / p.split_cols;
+      cc.c = col - q * p.split_cols;
+      cc.base += q * p.split_stride * (p.out_dt == IPN_BF16 ? 2 : 4);
     }
+  }
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[1][W]) {
+    float m[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) m[i] = 1.f;
     if (p.mul_mode != IPN_MUL_NONE) {
-      const long long mo = (long long)row * p.ld_mul + col0;
-      if (p.mul_mode == IPN_MUL_KEEP_MASK) {
-        const unsigned char* m = reinterpret_cast<const unsigned char*>(p.mul_src) + mo;
 #pragma unroll
-        for (int i = 0; i < W; ++i)
-          if (i < nvalid) v[i] *= (m[i] ? p.mul_scale : 0.f);
-      } else {
-        float y[W];
-        ld_act_n<W>(p.mul_src, mo, p.mul_dt, vec_ok(p.mul_src, p.ld_mul, p.mul_dt) && (col0 % 8 == 0), nvalid, y);
-#pragma unroll
-        for (int i = 0; i < W; ++i)
-          v[i] *= (p.mul_mode == IPN_MUL_SELU_GRAD) ? selu_grad_from_out(y[i]) : (y[i] > 0.f ? 1.f : 0.f);
+      for (int i = 0; i < W; ++i) {
+        if (i < nv) {
+          const long long mo = (long long)(row0 + i) * p.ld_mul + col;
+          if (p.mul_mode == IPN_MUL_KEEP_MASK) {
+            m[i] = reinterpret_cast<const unsigned char*>(p.mul_src)[mo] ? p.mul_scale : 0.f;
+          } else {
+            const float y = ld_act(p.mul_src, mo, p.mul_dt);
+            m[i] = (p.mul_mode == IPN_MUL_SELU_GRAD) ? selu_grad_from_out(y) : (y > 0.f ? 1.f : 0.f);
+          }
+        }
       }
     }
-    int c = col0;
-    char* base = reinterpret_cast<char*>(p.out);
-    if (p.split_cols > 0) {
-      const int q = col0 / p.split_cols;
-      c = col0 - q * p.split_cols;
-      base += q * p.split_stride * (p.out_dt == IPN_BF16 ? 2 : 4);
+    long long off[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      off[i] = (p.use_rowmap ? map_row(p.rowmap, row0 + i) : (long long)(row0 + i) * p.ld_out) + cc.c;
+    float old[W];
+    if (p.accumulate == IPN_RMW_ADD) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) old[i] = (i < nv) ? ld_act(cc.base, off[i], p.out_dt) : 0.f;
     }
-    const long long off = (p.use_rowmap ? map_row(p.rowmap, row) : (long long)row * p.ld_out) + c;
-    if (p.accumulate == IPN_STORE) {
-      const bool vec = (reinterpret_cast<uintptr_t>(base) % 16 == 0) && (off % 8 == 0);
-      st_act_n<W>(base, off, p.out_dt, vec, nvalid, v);
-    } else if (p.accumulate == IPN_ATOMIC_ADD) {
-      float* o = reinterpret_cast<float*>(base) + off;
 #pragma unroll
-      for (int i = 0; i < W; ++i)
-        if (i < nvalid) atomicAdd(o + i, v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < W; ++i)
-        if (i < nvalid) st_act(base, off + i, ld_act(base, off + i, p.out_dt) + v[i], p.out_dt);
+    for (int i = 0; i < W; ++i) {
+      if (i < nv) {
+        const float v = apply_act(acc[0][i] + cc.bias, p.act) * p.alpha * m[i];
+        if (p.accumulate == IPN_STORE) st_act(cc.base, off[i], v, p.out_dt);
+        else if (p.accumulate == IPN_ATOMIC_ADD) atomicAdd(reinterpret_cast<float*>(cc.base) + off[i], v);
+        else st_act(cc.base, off[i], old[i] + v, p.out_dt);
+      }
     }
   }
 };
@@ -107,74 +122,59 @@ struct EpiGruFwd {
     long long ld_final;
     int final_col0;
   };
-
+  struct Col {
+    float br, bz, bn;  // b_hh
+    float cr, cz, cn;  // constant part of the input projection (pvec)
+  };
+  static __device__ __forceinline__ void col_init(const Params& p, int col, Col& cc) {
+    const int H = p.H;
+    cc.br = p.b_hh[col]; cc.bz = p.b_hh[H + col]; cc.bn = p.b_hh[2 * H + col];
+    cc.cr = cc.cz = cc.cn = 0.f;
+    if (p.pvec != nullptr) { cc.cr = p.pvec[col]; cc.cz = p.pvec[H + col]; cc.cn = p.pvec[2 * H + col]; }
+  }
   template <int W>
-  static __device__ __forceinline__ void apply(const Params& p, int row, int col0, int nvalid, float (&acc)[3][W]) {
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[3][W]) {
     const int H = p.H, dt = p.act_dt;
-    const long long R = p.row0 + row;   // row inside the slot
-    const long long TR = p.trow + R;    // row in time-ordered buffers
-    const bool al = (col0 % 8 == 0) && (H % 8 == 0);
-    float pre[3][W];
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-      for (int i = 0; i < W; ++i) pre[g][i] = 0.f;
-    if (p.P != nullptr) {
-      const bool v = al && vec_ok(p.P, p.ldP, dt);
-      const long long PR = p.P_bcast ? R : TR;
-#pragma unroll
-      for (int g = 0; g < 3; ++g) ld_act_n<W>(p.P, PR * p.ldP + (long long)g * H + col0, dt, v, nvalid, pre[g]);
-    }
-    if (p.table != nullptr) {
-      const long long tk = p.tok[TR];
-      const bool v = al && vec_ok(p.table, p.ld_table, IPN_F32);
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        float t[W];
-        ld_act_n<W>(p.table, tk * p.ld_table + (long long)g * H + col0, IPN_F32, v, nvalid, t);
-#pragma unroll
-        for (int i = 0; i < W; ++i) pre[g][i] += t[i];
-      }
-    }
-    float hp[W];
-    ld_act_n<W>(p.h_prev, R * H + col0, dt, al && vec_ok(p.h_prev, H, dt), nvalid, hp);
-    float r[W], z[W], n[W], hn[W], h[W];
+    float pr[W], pz[W], pn[W], hp[W], mk[W];
+    // ---- phase 1: all loads
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      const int c = col0 + (i < nvalid ? i : 0);
-      float pr = pre[0][i], pz = pre[1][i], pn = pre[2][i];
-      if (p.pvec != nullptr) { pr += p.pvec[c]; pz += p.pvec[H + c]; pn += p.pvec[2 * H + c]; }
-      r[i] = sigmoid_acc(pr + acc[0][i] + p.b_hh[c]);
-      z[i] = sigmoid_acc(pz + acc[1][i] + p.b_hh[H + c]);
-      hn[i] = acc[2][i] + p.b_hh[2 * H + c];
-      n[i] = tanhf(pn + r[i] * hn[i]);
-      h[i] = (1.f - z[i]) * n[i] + z[i] * hp[i];
-    }
-    st_act_n<W>(p.h_out, R * H + col0, dt, al && vec_ok(p.h_out, H, dt), nvalid, h);
-    if (p.gates != nullptr) {
-      const bool v = al && vec_ok(p.gates, 4 * H, dt);
-      const long long go = TR * 4 * H + col0;
-      st_act_n<W>(p.gates, go, dt, v, nvalid, r);
-      st_act_n<W>(p.gates, go + H, dt, v, nvalid, z);
-      st_act_n<W>(p.gates, go + 2 * H, dt, v, nvalid, n);
-      st_act_n<W>(p.gates, go + 3 * H, dt, v, nvalid, hn);
-    }
-    if (p.y != nullptr) {
-      float yv[W];
-      if (p.mask != nullptr) {
-        const unsigned char* m = p.mask + TR * p.ld_mask + p.y_col0 + col0;
-#pragma unroll
-        for (int i = 0; i < W; ++i) yv[i] = (i < nvalid && m[i]) ? h[i] * p.mask_scale : 0.f;
-      } else {
-#pragma unroll
-        for (int i = 0; i < W; ++i) yv[i] = h[i];
+      pr[i] = cc.cr; pz[i] = cc.cz; pn[i] = cc.cn; hp[i] = 0.f; mk[i] = 1.f;
+      if (i < nv) {
+        const long long R = p.row0 + row0 + i, TR = p.trow + R;
+        if (p.P != nullptr) {
+          const long long o = (p.P_bcast ? R : TR) * p.ldP + col;
+          pr[i] += ld_act(p.P, o, dt); pz[i] += ld_act(p.P, o + H, dt); pn[i] += ld_act(p.P, o + 2 * H, dt);
+        }
+        if (p.table != nullptr) {
+          const long long o = (long long)p.tok[TR] * p.ld_table + col;
+          pr[i] += p.table[o]; pz[i] += p.table[o + H]; pn[i] += p.table[o + 2 * H];
+        }
+        hp[i] = ld_act(p.h_prev, R * H + col, dt);
+        if (p.y != nullptr && p.mask != nullptr) mk[i] = p.mask[TR * p.ld_mask + p.y_col0 + col] ? p.mask_scale : 0.f;
       }
-      st_act_n<W>(p.y, TR * p.ld_y + p.y_col0 + col0, dt, al && vec_ok(p.y, p.ld_y, dt) && (p.y_col0 % 8 == 0),
-                  nvalid, yv);
     }
-    if (p.final_out != nullptr)
-      st_act_n<W>(p.final_out, R * p.ld_final + p.final_col0 + col0, p.final_dt,
-                  al && vec_ok(p.final_out, p.ld_final, p.final_dt) && (p.final_col0 % 8 == 0), nvalid, h);
+    // ---- phase 2: gate math + stores
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (i < nv) {
+        const long long R = p.row0 + row0 + i, TR = p.trow + R;
+        const float r = sigmoid_acc(pr[i] + acc[0][i] + cc.br);
+        const float z = sigmoid_acc(pz[i] + acc[1][i] + cc.bz);
+        const float hn = acc[2][i] + cc.bn;
+        const float n = tanhf(pn[i] + r * hn);
+        const float h = (1.f - z) * n + z * hp[i];
+        st_act(p.h_out, R * H + col, h, dt);
+        if (p.gates != nullptr) {
+          const long long go = TR * 4 * H + col;
+          st_act(p.gates, go, r, dt); st_act(p.gates, go + H, z, dt);
+          st_act(p.gates, go + 2 * H, n, dt); st_act(p.gates, go + 3 * H, hn, dt);
+        }
+        if (p.y != nullptr) st_act(p.y, TR * p.ld_y + p.y_col0 + col, h * mk[i], dt);
+        if (p.final_out != nullptr) st_act(p.final_out, R * p.ld_final + p.final_col0 + col, h, p.final_dt);
+      }
+    }
   }
 };
 
@@ -201,55 +201,41 @@ struct GruBwdPoint {
 };
 
 template <int W>
-__device__ __forceinline__ void gru_bwd_pointwise(const GruBwdPoint& p, int row, int col0, int nvalid,
+__device__ __forceinline__ void gru_bwd_pointwise(const GruBwdPoint& p, int col, int row0, int nv,
                                                   const float (&dh_in)[W]) {
   const int H = p.H, dt = p.act_dt;
-  const long long R = p.row0 + row, TR = p.trow + R;
-  const bool al = (col0 % 8 == 0) && (H % 8 == 0);
-  float dh[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) dh[i] = dh_in[i];
-  if (p.dY != nullptr) {
-    float dy[W];
-    ld_act_n<W>(p.dY, TR * p.ld_dy + p.y_col0 + col0, dt, al && vec_ok(p.dY, p.ld_dy, dt) && (p.y_col0 % 8 == 0),
-                nvalid, dy);
-    if (p.mask != nullptr) {
-      const unsigned char* m = p.mask + TR * p.ld_mask + p.y_col0 + col0;
-#pragma unroll
-      for (int i = 0; i < W; ++i) dh[i] += (i < nvalid && m[i]) ? dy[i] * p.mask_scale : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < W; ++i) dh[i] += dy[i];
-    }
-  }
-  if (p.dh_n != nullptr) {
-#pragma unroll
-    for (int i = 0; i < W; ++i)
-      if (i < nvalid) dh[i] += p.dh_n[R * p.ld_dhn + col0 + i];
-  }
-  float r[W], z[W], n[W], hn[W], hp[W];
-  const bool vg = al && vec_ok(p.gates, 4 * H, dt);
-  const long long go = TR * 4 * H + col0;
-  ld_act_n<W>(p.gates, go, dt, vg, nvalid, r);
-  ld_act_n<W>(p.gates, go + H, dt, vg, nvalid, z);
-  ld_act_n<W>(p.gates, go + 2 * H, dt, vg, nvalid, n);
-  ld_act_n<W>(p.gates, go + 3 * H, dt, vg, nvalid, hn);
-  ld_act_n<W>(p.h_prev, R * H + col0, dt, al && vec_ok(p.h_prev, H, dt), nvalid, hp);
-  float dr[W], dz[W], dn[W], dgn[W], dhz[W];
+  float dh[W], r[W], z[W], n[W], hn[W], hp[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    dn[i] = dh[i] * (1.f - z[i]) * (1.f - n[i] * n[i]);
-    dz[i] = dh[i] * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
-    dr[i] = dn[i] * hn[i] * r[i] * (1.f - r[i]);
-    dgn[i] = dn[i] * r[i];
-    dhz[i] = dh[i] * z[i];
+    dh[i] = dh_in[i]; r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
+    if (i < nv) {
+      const long long R = p.row0 + row0 + i, TR = p.trow + R;
+      if (p.dY != nullptr) {
+        float dy = ld_act(p.dY, TR * p.ld_dy + p.y_col0 + col, dt);
+        if (p.mask != nullptr) dy = p.mask[TR * p.ld_mask + p.y_col0 + col] ? dy * p.mask_scale : 0.f;
+        dh[i] += dy;
+      }
+      if (p.dh_n != nullptr) dh[i] += p.dh_n[R * p.ld_dhn + col];
+      const long long go = TR * 4 * H + col;
+      r[i] = ld_act(p.gates, go, dt); z[i] = ld_act(p.gates, go + H, dt);
+      n[i] = ld_act(p.gates, go + 2 * H, dt); hn[i] = ld_act(p.gates, go + 3 * H, dt);
+      hp[i] = ld_act(p.h_prev, R * H + col, dt);
+    }
   }
-  const bool vp = al && vec_ok(p.dP, 3 * H, dt);
-  st_act_n<W>(p.dP, TR * 3 * H + col0, dt, vp, nvalid, dr);
-  st_act_n<W>(p.dP, TR * 3 * H + H + col0, dt, vp, nvalid, dz);
-  st_act_n<W>(p.dP, TR * 3 * H + 2 * H + col0, dt, vp, nvalid, dn);
-  st_act_n<W>(p.dGn, TR * H + col0, dt, al && vec_ok(p.dGn, H, dt), nvalid, dgn);
-  st_act_n<W>(p.dhz_out, R * H + col0, IPN_F32, al && vec_ok(p.dhz_out, H, IPN_F32), nvalid, dhz);
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (i < nv) {
+      const long long R = p.row0 + row0 + i, TR = p.trow + R;
+      const float dn = dh[i] * (1.f - z[i]) * (1.f - n[i] * n[i]);
+      const float dz = dh[i] * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
+      const float dr = dn * hn[i] * r[i] * (1.f - r[i]);
+      st_act(p.dP, TR * 3 * H + col, dr, dt);
+      st_act(p.dP, TR * 3 * H + H + col, dz, dt);
+      st_act(p.dP, TR * 3 * H + 2 * H + col, dn, dt);
+      st_act(p.dGn, TR * H + col, dn * r[i], dt);
+      p.dhz_out[R * H + col] = dh[i] * z[i];
+    }
+  }
 }
 
 // GEMM epilogue: acc = ([dP_r, dP_z | dGn] W_hh)[row, col] of step s  ->  dh wrt the state that entered
@@ -266,33 +252,33 @@ struct EpiGruBwd {
     const void* h0;  // slot base of h0 (act_dt), for SELU'
     GruBwdPoint pw;  // describes step s-1 (unused when is_first_step)
   };
-
+  struct Col {};
+  static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
   template <int W>
-  static __device__ __forceinline__ void apply(const Params& p, int row, int col0, int nvalid, float (&acc)[1][W]) {
+  static __device__ __forceinline__ void applyT(const Params& p, const Col&, int col, int row0, int nv,
+                                                float (&acc)[1][W]) {
     const int H = p.pw.H;
-    const long long R = p.pw.row0 + row;
     float dh[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) dh[i] = acc[0][i];
-    if (p.dhz_in != nullptr) {
-      float t[W];
-      ld_act_n<W>(p.dhz_in, R * H + col0, IPN_F32, (col0 % 4 == 0) && vec_ok(p.dhz_in, H, IPN_F32), nvalid, t);
-#pragma unroll
-      for (int i = 0; i < W; ++i) dh[i] += t[i];
+    for (int i = 0; i < W; ++i) {
+      dh[i] = acc[0][i];
+      if (p.dhz_in != nullptr && i < nv) dh[i] += p.dhz_in[(long long)(p.pw.row0 + row0 + i) * H + col];
     }
     if (p.is_first_step) {
       if (p.dh0 != nullptr) {
-        if (p.dh0_selu) {
-          float h0[W];
-          ld_act_n<W>(p.h0, R * H + col0, p.pw.act_dt, false, nvalid, h0);
 #pragma unroll
-          for (int i = 0; i < W; ++i) dh[i] *= selu_grad_from_out(h0[i]);
+        for (int i = 0; i < W; ++i) {
+          if (i < nv) {
+            const long long R = p.pw.row0 + row0 + i;
+            float v = dh[i];
+            if (p.dh0_selu) v *= selu_grad_from_out(ld_act(p.h0, R * H + col, p.pw.act_dt));
+            st_act(p.dh0, R * p.ld_dh0 + col, v, p.dh0_dt);
+          }
         }
-        st_act_n<W>(p.dh0, R * p.ld_dh0 + col0, p.dh0_dt, false, nvalid, dh);
       }
       return;
     }
-    gru_bwd_pointwise<W>(p.pw, row, col0, nvalid, dh);
+    gru_bwd_pointwise<W>(p.pw, col, row0, nv, dh);
   }
 };
 
@@ -315,42 +301,50 @@ struct EpiLstmFwd {
     long long ld_y;
     int y_col0;
   };
-  template <int W>
-  static __device__ __forceinline__ void apply(const Params& p, int row, int col0, int nvalid, float (&acc)[4][W]) {
-    const int H = p.H, dt = p.act_dt;
-    const long long R = row, TR = p.trow + row;
-    const bool al = (col0 % 8 == 0) && (H % 8 == 0);
-    float pre[4][W];
-    const bool v = al && vec_ok(p.P, p.ldP, dt);
+  struct Col {
+    float b[4];
+  };
+  static __device__ __forceinline__ void col_init(const Params& p, int col, Col& cc) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) ld_act_n<W>(p.P, TR * p.ldP + (long long)g * H + col0, dt, v, nvalid, pre[g]);
-    float cp[W];
-    ld_act_n<W>(p.c_prev, R * H + col0, IPN_F32, al && vec_ok(p.c_prev, H, IPN_F32), nvalid, cp);
-    float gi[W], gf[W], gg[W], go[W], c[W], h[W];
+    for (int g = 0; g < 4; ++g) cc.b[g] = p.b_hh != nullptr ? p.b_hh[g * p.H + col] : 0.f;
+  }
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[4][W]) {
+    const int H = p.H, dt = p.act_dt;
+    float pre[4][W], cp[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      const int cc = col0 + (i < nvalid ? i : 0);
-      float bi = 0.f, bf = 0.f, bg = 0.f, bo = 0.f;
-      if (p.b_hh != nullptr) { bi = p.b_hh[cc]; bf = p.b_hh[H + cc]; bg = p.b_hh[2 * H + cc]; bo = p.b_hh[3 * H + cc]; }
-      gi[i] = sigmoid_acc(pre[0][i] + acc[0][i] + bi);
-      gf[i] = sigmoid_acc(pre[1][i] + acc[1][i] + bf);
-      gg[i] = tanhf(pre[2][i] + acc[2][i] + bg);
-      go[i] = sigmoid_acc(pre[3][i] + acc[3][i] + bo);
-      c[i] = gf[i] * cp[i] + gi[i] * gg[i];
-      h[i] = go[i] * tanhf(c[i]);
+      cp[i] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pre[g][i] = 0.f;
+      if (i < nv) {
+        const long long R = row0 + i, TR = p.trow + R;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[g][i] = ld_act(p.P, TR * p.ldP + (long long)g * H + col, dt);
+        cp[i] = p.c_prev[R * H + col];
+      }
     }
-    st_act_n<W>(p.c_out, R * H + col0, IPN_F32, al && vec_ok(p.c_out, H, IPN_F32), nvalid, c);
-    st_act_n<W>(p.h_out, R * H + col0, dt, al && vec_ok(p.h_out, H, dt), nvalid, h);
-    if (p.gates != nullptr) {
-      const bool vg = al && vec_ok(p.gates, 4 * H, dt);
-      const long long o = TR * 4 * H + col0;
-      st_act_n<W>(p.gates, o, dt, vg, nvalid, gi);
-      st_act_n<W>(p.gates, o + H, dt, vg, nvalid, gf);
-      st_act_n<W>(p.gates, o + 2 * H, dt, vg, nvalid, gg);
-      st_act_n<W>(p.gates, o + 3 * H, dt, vg, nvalid, go);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (i < nv) {
+        const long long R = row0 + i, TR = p.trow + R;
+        const float gi = sigmoid_acc(pre[0][i] + acc[0][i] + cc.b[0]);
+        const float gf = sigmoid_acc(pre[1][i] + acc[1][i] + cc.b[1]);
+        const float gg = tanhf(pre[2][i] + acc[2][i] + cc.b[2]);
+        const float go = sigmoid_acc(pre[3][i] + acc[3][i] + cc.b[3]);
+        const float c = gf * cp[i] + gi * gg;
+        const float h = go * tanhf(c);
+        p.c_out[R * H + col] = c;
+        st_act(p.h_out, R * H + col, h, dt);
+        if (p.gates != nullptr) {
+          const long long o = TR * 4 * H + col;
+          st_act(p.gates, o, gi, dt); st_act(p.gates, o + H, gf, dt);
+          st_act(p.gates, o + 2 * H, gg, dt); st_act(p.gates, o + 3 * H, go, dt);
+        }
+        if (p.y != nullptr) st_act(p.y, TR * p.ld_y + p.y_col0 + col, h, dt);
+      }
     }
-    if (p.y != nullptr)
-      st_act_n<W>(p.y, TR * p.ld_y + p.y_col0 + col0, dt, al && vec_ok(p.y, p.ld_y, dt) && (p.y_col0 % 8 == 0), nvalid, h);
   }
 };
 
@@ -371,53 +365,37 @@ struct LstmBwdPoint {
 };
 
 template <int W>
-__device__ __forceinline__ void lstm_bwd_pointwise(const LstmBwdPoint& p, int row, int col0, int nvalid,
+__device__ __forceinline__ void lstm_bwd_pointwise(const LstmBwdPoint& p, int col, int row0, int nv,
                                                    const float (&dh_in)[W]) {
   const int H = p.H, dt = p.act_dt;
-  const long long R = row, TR = p.trow + row;
-  const bool al = (col0 % 8 == 0) && (H % 8 == 0);
-  float dh[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) dh[i] = dh_in[i];
-  if (p.dY != nullptr) {
-    float dy[W];
-    ld_act_n<W>(p.dY, TR * p.ld_dy + p.y_col0 + col0, dt, al && vec_ok(p.dY, p.ld_dy, dt) && (p.y_col0 % 8 == 0),
-                nvalid, dy);
-#pragma unroll
-    for (int i = 0; i < W; ++i) dh[i] += dy[i];
-  }
-  float gi[W], gf[W], gg[W], go[W], cp[W], cc[W], dci[W];
-  const bool vg = al && vec_ok(p.gates, 4 * H, dt);
-  const long long o = TR * 4 * H + col0;
-  ld_act_n<W>(p.gates, o, dt, vg, nvalid, gi);
-  ld_act_n<W>(p.gates, o + H, dt, vg, nvalid, gf);
-  ld_act_n<W>(p.gates, o + 2 * H, dt, vg, nvalid, gg);
-  ld_act_n<W>(p.gates, o + 3 * H, dt, vg, nvalid, go);
-  const bool vf = al && vec_ok(p.c_prev, H, IPN_F32);
-  ld_act_n<W>(p.c_prev, R * H + col0, IPN_F32, vf, nvalid, cp);
-  ld_act_n<W>(p.c_cur, R * H + col0, IPN_F32, vf, nvalid, cc);
-  if (p.dc_in != nullptr) ld_act_n<W>(p.dc_in, R * H + col0, IPN_F32, vf, nvalid, dci);
-  else {
-#pragma unroll
-    for (int i = 0; i < W; ++i) dci[i] = 0.f;
-  }
-  float di[W], df[W], dg[W], dob[W], dco[W];
+  float dh[W], gi[W], gf[W], gg[W], go[W], cp[W], cc[W], dci[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    const float tc = tanhf(cc[i]);
-    const float dc = dci[i] + dh[i] * go[i] * (1.f - tc * tc);
-    dob[i] = dh[i] * tc * go[i] * (1.f - go[i]);
-    di[i] = dc * gg[i] * gi[i] * (1.f - gi[i]);
-    df[i] = dc * cp[i] * gf[i] * (1.f - gf[i]);
-    dg[i] = dc * gi[i] * (1.f - gg[i] * gg[i]);
-    dco[i] = dc * gf[i];
+    dh[i] = dh_in[i]; gi[i] = gf[i] = gg[i] = go[i] = cp[i] = cc[i] = dci[i] = 0.f;
+    if (i < nv) {
+      const long long R = row0 + i, TR = p.trow + R;
+      if (p.dY != nullptr) dh[i] += ld_act(p.dY, TR * p.ld_dy + p.y_col0 + col, dt);
+      const long long o = TR * 4 * H + col;
+      gi[i] = ld_act(p.gates, o, dt); gf[i] = ld_act(p.gates, o + H, dt);
+      gg[i] = ld_act(p.gates, o + 2 * H, dt); go[i] = ld_act(p.gates, o + 3 * H, dt);
+      cp[i] = p.c_prev[R * H + col]; cc[i] = p.c_cur[R * H + col];
+      if (p.dc_in != nullptr) dci[i] = p.dc_in[R * H + col];
+    }
   }
-  const bool vp = al && vec_ok(p.dP, 4 * H, dt);
-  st_act_n<W>(p.dP, o, dt, vp, nvalid, di);
-  st_act_n<W>(p.dP, o + H, dt, vp, nvalid, df);
-  st_act_n<W>(p.dP, o + 2 * H, dt, vp, nvalid, dg);
-  st_act_n<W>(p.dP, o + 3 * H, dt, vp, nvalid, dob);
-  st_act_n<W>(p.dc_out, R * H + col0, IPN_F32, vf, nvalid, dco);
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (i < nv) {
+      const long long R = row0 + i, TR = p.trow + R;
+      const float tc = tanhf(cc[i]);
+      const float dc = dci[i] + dh[i] * go[i] * (1.f - tc * tc);
+      const long long o = TR * 4 * H + col;
+      st_act(p.dP, o, dc * gg[i] * gi[i] * (1.f - gi[i]), dt);
+      st_act(p.dP, o + H, dc * cp[i] * gf[i] * (1.f - gf[i]), dt);
+      st_act(p.dP, o + 2 * H, dc * gi[i] * (1.f - gg[i] * gg[i]), dt);
+      st_act(p.dP, o + 3 * H, dh[i] * tc * go[i] * (1.f - go[i]), dt);
+      p.dc_out[R * H + col] = dc * gf[i];
+    }
+  }
 }
 
 // GEMM epilogue: acc = (dP[s] W_hh)[row, col] = gradient wrt h_{s-1} from the recurrence.
@@ -427,13 +405,16 @@ struct EpiLstmBwd {
     int is_first_step;  // nothing earlier to differentiate
     LstmBwdPoint pw;    // step s-1
   };
+  struct Col {};
+  static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
   template <int W>
-  static __device__ __forceinline__ void apply(const Params& p, int row, int col0, int nvalid, float (&acc)[1][W]) {
+  static __device__ __forceinline__ void applyT(const Params& p, const Col&, int col, int row0, int nv,
+                                                float (&acc)[1][W]) {
     if (p.is_first_step) return;
     float dh[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) dh[i] = acc[0][i];
-    lstm_bwd_pointwise<W>(p.pw, row, col0, nvalid, dh);
+    lstm_bwd_pointwise<W>(p.pw, col, row0, nv, dh);
   }
 };
 

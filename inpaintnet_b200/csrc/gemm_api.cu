@@ -23,9 +23,10 @@ static int fill_linear_epi(EpiLinear::Params& e, const IpnGemm* g) {
   return IPN_OK;
 }
 
-template <int BNG, bool TA, bool TB>
+// API operands: A = activations [M,K] (output rows), B = weights [N,K] (output columns).
+template <int BR, bool TW, bool TX>
 static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
-  using Cfg = UmmaCfg<1, BNG, TA, TB>;
+  using Cfg = UmmaCfg<1, BR, TW, TX>;
   UmmaBatch<EpiLinear> b;
   memset(&b, 0, sizeof(b));
   b.split_k = split_k;
@@ -36,12 +37,13 @@ static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
   P.gate_stride = 0;
   for (int s = 0; s < g->nseg; ++s) {
     const IpnGemmSeg& sg = g->seg[s];
-    HostOperand a{sg.A, sg.lda, sg.transA, g->M, 0, 0};
-    HostOperand bb{sg.B, sg.ldb, sg.transB, g->N, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[s], a, bb, sg.K, BNG));
+    HostOperand x{sg.A, sg.lda, sg.transA, g->M, 0, 0};
+    HostOperand w{sg.B, sg.ldb, sg.transB, g->N, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[s], x, w, sg.K, BR));
   }
   fill_linear_epi(P.epi, g);
-  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream, TA ? "gemm_umma_tn_wgrad" : (TB ? "gemm_umma_nn_dgrad" : "gemm_umma_nt"));
+  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream,
+                                     TX ? "gemm_umma_tn_wgrad" : (TW ? "gemm_umma_nn_dgrad" : "gemm_umma_nt"));
 }
 
 static int pick_split_k(const IpnGemm* g, int tile_m, int tile_n, int bk) {
@@ -101,16 +103,23 @@ extern "C" int ipn_gemm(const IpnGemm* g, void* stream_) {
   const int tA = g->seg[0].transA, tB = g->seg[0].transB;
   for (int s = 1; s < g->nseg; ++s)
     IPN_REQUIRE(g->seg[s].transA == tA && g->seg[s].transB == tB, IPN_ERR_ARG, "ipn_gemm: segments must share layouts");
-  const int tn = (!tA && !tB) ? (g->N <= 64 ? 64 : (g->N >= 512 ? 256 : 128)) : 128;
-  const int split = pick_split_k(g, UMMA_BM, tn, UMMA_BK);
+  // rows per tile: 256 for tall problems, 128 otherwise, 64 for short ones (more CTAs)
+  const int br = (tA ? (g->M >= 1024 ? 256 : 128) : (g->M >= 4096 ? 256 : (g->M > 64 ? 128 : 64)));
+  const int split = pick_split_k(g, br, UMMA_BC, UMMA_BK);
   if (split > 1) IPN_REQUIRE(!g->bias && g->act == IPN_ACT_NONE, IPN_ERR_ARG, "split_k with bias/act");
   if (!tA && !tB) {
-    if (tn == 64) return gemm_umma<64, false, false>(g, split, stream);
-    if (tn == 256) return gemm_umma<256, false, false>(g, split, stream);
+    if (br == 64) return gemm_umma<64, false, false>(g, split, stream);
+    if (br == 256) return gemm_umma<256, false, false>(g, split, stream);
     return gemm_umma<128, false, false>(g, split, stream);
   }
-  if (!tA && tB) return gemm_umma<128, false, true>(g, split, stream);
-  if (tA && tB) return gemm_umma<128, true, true>(g, split, stream);
+  if (!tA && tB) {
+    if (br == 256) return gemm_umma<256, true, false>(g, split, stream);
+    return gemm_umma<128, true, false>(g, split, stream);
+  }
+  if (tA && tB) {
+    if (br == 256) return gemm_umma<256, true, true>(g, split, stream);
+    return gemm_umma<128, true, true>(g, split, stream);
+  }
   ipn::set_error("ipn_gemm: layout transA=1,transB=0 is not provided by the tcgen05 core");
   return IPN_ERR_ARG;
 }

@@ -112,17 +112,21 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const __grid_constant__ 
 
   const int col0 = n0 + tx * 4;
   if (col0 >= P.N) return;
-  const int nvalid = min(4, P.N - col0);
+  const int row0 = m0 + ty * 4;
+  if (row0 >= P.M) return;
+  const int nv = min(4, P.M - row0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = m0 + ty * 4 + i;
-    if (row >= P.M) continue;
+  for (int j = 0; j < 4; ++j) {
+    const int col = col0 + j;
+    if (col >= P.N) break;
+    typename Epi::Col cc;
+    Epi::col_init(P.epi, col, cc);
     float a[G][4];
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[g][j] = acc[g][i][j];
-    Epi::template apply<4>(P.epi, row, col0, nvalid, a);
+      for (int i = 0; i < 4; ++i) a[g][i] = acc[g][i][j];
+    Epi::template applyT<4>(P.epi, cc, col, row0, nv, a);
   }
 }
 

@@ -1,35 +1,43 @@
-// tcgen05 (UMMA) GEMM core: D[128 x G*BNG tile] accumulated in TMEM from TMA-fed SWIZZLE_128B
-// shared-memory stages, warp specialised (warp0 = TMA producer, warp1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue, one TMEM lane == one output row per thread).  bf16 x bf16 -> fp32.
+// tcgen05 (UMMA) GEMM core, "lanes = output columns" formulation.
 //
-//   D[m, g, n] = sum_seg sum_k A_seg[m, k] * B_seg[g*gate_stride + n, k]
+//   D[row, g, col] = sum_seg sum_k X_seg[row, k] * W_seg[g*gate_stride + col, k]
 //
-// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) independently,
-// so forward (NT), dgrad (NN) and wgrad (TN) GEMMs all run without materialised transposes.
+// The WEIGHT-side operand W feeds the M dimension of the MMA (128 TMEM lanes = 128 output columns),
+// the ACTIVATION-side operand X feeds the N dimension (BR output rows = BR TMEM columns per gate), so in
+// the epilogue a warp's 32 lanes own 32 consecutive output columns of the same row: all global traffic
+// of the epilogue is coalesced without shared-memory staging (see epilogues.cuh).  Gate g of a recurrent
+// cell is a separate accumulator (TMEM columns [g*BR, (g+1)*BR)) fed by its own W sub-tile, so one thread
+// holds r, z, n (or i, f, g, o) of the same hidden unit.
+//
+// warp 0 = TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier expect_tx), warp 1 = MMA issuer
+// (single thread, tcgen05.mma kind::f16, fp32 accumulate in TMEM) + TMEM owner, warps 2..9 = epilogue
+// (tcgen05.ld 32x32b.x16).  Both operands may be K-major or MN-major independently, so forward (NT), dgrad
+// (NN) and wgrad (TN) GEMMs run without materialised transposes.  Up to two K segments and two
+// independent problems per launch; split-K across CTAs for the weight gradients.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace ipn {
 
-constexpr int UMMA_BM = 128;
-constexpr int UMMA_BK = 64;  // bf16 elements per stage along K (= 128 bytes, one swizzle row)
+constexpr int UMMA_BC = 128;       // output columns per tile (TMEM lanes, MMA M)
+constexpr int UMMA_BK = 64;        // bf16 elements per stage along K (= 128 bytes, one swizzle row)
 constexpr int UMMA_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 warps per TMEM lane quadrant)
 
 struct UmmaSeg {
-  alignas(64) CUtensorMap tmA;
-  alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmW;
+  alignas(64) CUtensorMap tmX;
   int K;
-  int a_c0, a_c1;  // base coordinates (inner, outer) added to the tile coordinates
-  int b_c0, b_c1;
+  int w_c0, w_c1;  // base coordinates (inner, outer) added to the tile coordinates
+  int x_c0, x_c1;
 };
 
 template <class Epi>
 struct UmmaProblem {
   UmmaSeg seg[2];
   int nseg;
-  int M, N;         // N = columns per gate
-  int gate_stride;  // row (K-major B) / column (MN-major B) distance between gates
+  int M, N;         // M = output rows (X side), N = output columns per gate (W side)
+  int gate_stride;  // row (K-major W) / column (MN-major W) distance between gates
   typename Epi::Params epi;
 };
 
@@ -39,32 +47,33 @@ struct UmmaBatch {
   int split_k;
 };
 
-template <int G_, int BNG_, bool TA_, bool TB_>
+// G gates, BR output rows per tile, TW / TX: W / X operand is MN-major (row-major [K, cols|rows])
+template <int G_, int BR_, bool TW_, bool TX_, int MAX_SMEM_KB = 110>
 struct UmmaCfg {
   static constexpr int G = G_;
-  static constexpr int BNG = BNG_;
-  static constexpr bool TA = TA_;
-  static constexpr bool TB = TB_;
-  static constexpr int BN = G_ * BNG_;
-  static constexpr int A_BYTES = UMMA_BM * UMMA_BK * 2;
-  static constexpr int B_BYTES = BN * UMMA_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // Two CTAs per SM: one CTA's epilogue (global-memory latency bound) overlaps the other's mainloop and
-  // the memory-level parallelism per SM doubles.  ~110 KB of stages per CTA, at least 2 stages.
-  static constexpr int MAX_SMEM = 110 * 1024;
-  static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int BR = BR_;
+  static constexpr bool TW = TW_;
+  static constexpr bool TX = TX_;
+  static constexpr int W_BYTES = G_ * UMMA_BC * UMMA_BK * 2;
+  static constexpr int X_BYTES = BR_ * UMMA_BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
+  static constexpr int STAGES_RAW = (MAX_SMEM_KB * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256] for M=128");
-  static_assert(!TB_ || (BNG_ % 64 == 0), "MN-major B needs 64-wide blocks");
-  static_assert(BNG_ % 16 == 0, "epilogue works on 16-column chunks");
+  static constexpr int ACC_COLS = G_ * BR_;
+  static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
+  static_assert(BR_ % 16 == 0 && BR_ >= 16 && BR_ <= 256, "UMMA N must be a multiple of 16 in [16,256] for M=128");
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(!TX_ || (BR_ % 64 == 0), "MN-major X needs 64-wide blocks");
+  static_assert(SMEM_BYTES <= 227 * 1024, "stage configuration exceeds shared memory");
 };
 
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
+__global__ void __launch_bounds__(UMMA_THREADS, Cfg::CTAS_PER_SM)
+umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   static_assert(Epi::G == Cfg::G, "epilogue / tile gate count mismatch");
-  constexpr int G = Cfg::G, BNG = Cfg::BNG, BN = Cfg::BN, STAGES = Cfg::STAGES;
+  constexpr int G = Cfg::G, BR = Cfg::BR, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -77,12 +86,12 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
   const int prob = blockIdx.z / batch.split_k;
   const int ksplit = blockIdx.z - prob * batch.split_k;
   const UmmaProblem<Epi>& P = batch.p[prob];
-  const int n0 = blockIdx.x * BNG;
-  const int m0 = blockIdx.y * UMMA_BM;
+  const int c0 = blockIdx.x * UMMA_BC;  // first output column of this tile
+  const int r0 = blockIdx.y * BR;       // first output row
 
   // k-chunk range handled by this CTA (over the concatenation of all segments)
-  int chunks_seg0 = (P.seg[0].K + UMMA_BK - 1) / UMMA_BK;
-  int chunks_total = chunks_seg0 + (P.nseg > 1 ? (P.seg[1].K + UMMA_BK - 1) / UMMA_BK : 0);
+  const int chunks_seg0 = (P.seg[0].K + UMMA_BK - 1) / UMMA_BK;
+  const int chunks_total = chunks_seg0 + (P.nseg > 1 ? (P.seg[1].K + UMMA_BK - 1) / UMMA_BK : 0);
   const int per = (chunks_total + batch.split_k - 1) / batch.split_k;
   const int kc_begin = ksplit * per;
   const int kc_end = min(chunks_total, kc_begin + per);
@@ -101,11 +110,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
     ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     ptx::tmem_relinquish();
   } else if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&P.seg[0].tmA);
-    ptx::prefetch_tmap(&P.seg[0].tmB);
+    ptx::prefetch_tmap(&P.seg[0].tmW);
+    ptx::prefetch_tmap(&P.seg[0].tmX);
     if (P.nseg > 1) {
-      ptx::prefetch_tmap(&P.seg[1].tmA);
-      ptx::prefetch_tmap(&P.seg[1].tmB);
+      ptx::prefetch_tmap(&P.seg[1].tmW);
+      ptx::prefetch_tmap(&P.seg[1].tmX);
     }
   }
   ptx::tc_fence_before();
@@ -123,28 +132,26 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
         const UmmaSeg& S = P.seg[si];
         const int k0 = (si ? kc - chunks_seg0 : kc) * UMMA_BK;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
+        uint8_t* sw = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sx = sw + Cfg::W_BYTES;
         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        if (!Cfg::TA) {
-          ptx::tma_load_2d(sa, &S.tmA, &full_bar[stage], S.a_c0 + k0, S.a_c1 + m0);
-        } else {
 #pragma unroll
-          for (int i = 0; i < UMMA_BM / 64; ++i)
-            ptx::tma_load_2d(sa + i * 8192, &S.tmA, &full_bar[stage], S.a_c0 + m0 + 64 * i, S.a_c1 + k0);
+        for (int g = 0; g < G; ++g) {
+          if (!Cfg::TW) {
+            ptx::tma_load_2d(sw + g * 16384, &S.tmW, &full_bar[stage], S.w_c0 + k0, S.w_c1 + g * P.gate_stride + c0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < UMMA_BC / 64; ++i)
+              ptx::tma_load_2d(sw + g * 16384 + i * 8192, &S.tmW, &full_bar[stage],
+                               S.w_c0 + g * P.gate_stride + c0 + 64 * i, S.w_c1 + k0);
+          }
         }
-        if (!Cfg::TB) {
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            ptx::tma_load_2d(sb + g * BNG * 128, &S.tmB, &full_bar[stage], S.b_c0 + k0,
-                             S.b_c1 + g * P.gate_stride + n0);
+        if (!Cfg::TX) {
+          ptx::tma_load_2d(sx, &S.tmX, &full_bar[stage], S.x_c0 + k0, S.x_c1 + r0);
         } else {
 #pragma unroll
-          for (int g = 0; g < G; ++g)
-#pragma unroll
-            for (int i = 0; i < BNG / 64; ++i)
-              ptx::tma_load_2d(sb + (g * (BNG / 64) + i) * 8192, &S.tmB, &full_bar[stage],
-                               S.b_c0 + g * P.gate_stride + n0 + 64 * i, S.b_c1 + k0);
+          for (int i = 0; i < BR / 64; ++i)
+            ptx::tma_load_2d(sx + i * 8192, &S.tmX, &full_bar[stage], S.x_c0 + r0 + 64 * i, S.x_c1 + k0);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -152,21 +159,24 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && nchunks > 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(UMMA_BM, BN, Cfg::TA ? 1 : 0, Cfg::TB ? 1 : 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(UMMA_BC, BR, Cfg::TW ? 1 : 0, Cfg::TX ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < nchunks; ++kc) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint32_t sw = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sx = sw + Cfg::W_BYTES;
 #pragma unroll
         for (int kk = 0; kk < UMMA_BK / 16; ++kk) {
-          const uint64_t da = Cfg::TA ? ptx::make_smem_desc(sa + kk * 2048, 8192, 1024)
-                                      : ptx::make_smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t db = Cfg::TB ? ptx::make_smem_desc(sb + kk * 2048, 8192, 1024)
-                                      : ptx::make_smem_desc(sb + kk * 32, 16, 1024);
-          ptx::umma_bf16(tmem_base, da, db, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t dx = Cfg::TX ? ptx::make_smem_desc(sx + kk * 2048, 8192, 1024)
+                                      : ptx::make_smem_desc(sx + kk * 32, 16, 1024);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const uint64_t dw = Cfg::TW ? ptx::make_smem_desc(sw + g * 16384 + kk * 2048, 8192, 1024)
+                                        : ptx::make_smem_desc(sw + g * 16384 + kk * 32, 16, 1024);
+            ptx::umma_bf16(tmem_base + (uint32_t)(g * BR), dw, dx, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -175,22 +185,25 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    const int q = warp & 3;          // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 16-column chunks
-    const int row = m0 + q * 32 + lane;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 16-row chunks
+    const int col = c0 + q * 32 + lane;
+    const bool col_ok = col < P.N;
+    typename Epi::Col cc;
+    if (col_ok) Epi::col_init(P.epi, col, cc);  // overlaps the mainloop
     if (nchunks > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
 #pragma unroll 1
-    for (int c = half; c < BNG / 16; c += 2) {
-      const int col0 = n0 + c * 16;
-      if (col0 >= P.N) break;  // warp uniform
+    for (int c = half; c < BR / 16; c += 2) {
+      const int row0 = r0 + c * 16;
+      if (row0 >= P.M) break;  // warp uniform
       float acc[G][16];
       if (nchunks > 0) {
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BNG + c * 16), acc[g]);
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BR + c * 16), acc[g]);
         ptx::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -198,7 +211,20 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) umma_gemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
       }
-      if (row < P.M) Epi::template apply<16>(P.epi, row, col0, min(16, P.N - col0), acc);
+      if (col_ok) {
+        const int nv = min(16, P.M - row0);
+        // two halves of 8 rows: bounds the registers held by the epilogue's load phase
+        float a8[G][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a8[g][i] = acc[g][h * 8 + i];
+          const int nvh = nv - h * 8;
+          if (nvh > 0) Epi::template applyT<8>(P.epi, cc, col, row0 + h * 8, min(8, nvh), a8);
+        }
+      }
     }
   }
   ptx::tc_fence_before();

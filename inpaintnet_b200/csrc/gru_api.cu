@@ -6,16 +6,17 @@ namespace ipn {
 
 template <int W>
 __global__ void gru_bwd_point_kernel(GruBwdPoint p0, GruBwdPoint p1, int nrows) {
+  // thread = (column, chunk of W rows): consecutive threads -> consecutive columns (coalesced)
   const GruBwdPoint& p = blockIdx.z == 0 ? p0 : p1;
-  const int chunks = (p.H + W - 1) / W;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nrows * chunks) return;
-  const int row = (int)(idx / chunks);
-  const int col0 = (int)(idx % chunks) * W;
+  const int rchunks = (nrows + W - 1) / W;
+  if (idx >= (long long)rchunks * p.H) return;
+  const int col = (int)(idx % p.H);
+  const int row0 = (int)(idx / p.H) * W;
   float dh[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) dh[i] = 0.f;
-  gru_bwd_pointwise<W>(p, row, col0, min(W, p.H - col0), dh);
+  gru_bwd_pointwise<W>(p, col, row0, min(W, nrows - row0), dh);
 }
 
 static inline const char* slot_ptr(const void* base, long long slot, long long B_total, int H, int dt) {
@@ -94,7 +95,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     return IPN_OK;
   }
 
-  using Cfg = UmmaCfg<3, 64, false, false>;
+  using Cfg = UmmaCfg<3, 128, false, false, 200>;   // 128 units x 128 rows x 3 gates: 384 TMEM columns, 1 CTA/SM
   UmmaBatch<EpiGruFwd> b;
   memset(&b, 0, sizeof(b));
   b.split_k = 1;
@@ -104,12 +105,12 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     P.nseg = 1; P.M = L->nrows; P.N = H; P.gate_stride = H;
     HostOperand a{D.hseq, H, 0, (long long)(T + 1) * Bt, 0, 0};
     HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BNG));
+    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BR));
   }
   for (int s = L->s_begin; s < L->s_end; ++s) {
     for (int d = 0; d < L->ndir; ++d) {
       const int in_slot = fill_epi(b.p[d].epi, L->dir[d], s);
-      b.p[d].seg[0].a_c1 = (int)(in_slot * Bt + L->row0);
+      b.p[d].seg[0].x_c1 = (int)(in_slot * Bt + L->row0);
     }
     IPN_PROPAGATE((launch_umma<Cfg, EpiGruFwd>(b, L->ndir, L->nrows, H, stream, "gru_step_fwd_umma")));
   }
@@ -152,7 +153,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     fill_point(p0, 0, T - 1);
     if (L->ndir > 1) fill_point(p1, 1, T - 1); else p1 = p0;
     constexpr int W = 4;
-    const long long work = (long long)L->nrows * ((H + W - 1) / W);
+    const long long work = (long long)((L->nrows + W - 1) / W) * H;
     dim3 grid(cdiv(work, 256), 1, L->ndir);
     ProfScope prof("gru_bwd_pointwise", 0.0, 0.0, stream);
     gru_bwd_point_kernel<W><<<grid, 256, 0, stream>>>(p0, p1, L->nrows);
@@ -192,7 +193,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     return IPN_OK;
   }
 
-  using Cfg = UmmaCfg<1, 128, false, true>;
+  using Cfg = UmmaCfg<1, 128, true, false>;   // W_hh read MN-major (columns = hidden units on the TMEM lanes)
   UmmaBatch<EpiGruBwd> b;
   memset(&b, 0, sizeof(b));
   b.split_k = 1;
@@ -202,16 +203,16 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0;
     HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, 0, 0};
     HostOperand w0{D.w_hh, H, 1, H, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a0, w0, 2 * H, Cfg::BNG));
+    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a0, w0, 2 * H, Cfg::BR));
     HostOperand a1{D.dGn, H, 0, (long long)T * Bt, 0, 0};
     HostOperand w1{D.w_hh, H, 1, H, 0, 2LL * H};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[1], a1, w1, H, Cfg::BNG));
+    IPN_PROPAGATE(fill_umma_seg(P.seg[1], a1, w1, H, Cfg::BR));
   }
   for (int s = T - 1; s >= 0; --s) {
     for (int d = 0; d < L->ndir; ++d) {
       const int t = L->dir[d].reverse ? T - 1 - s : s;
-      b.p[d].seg[0].a_c1 = (int)(t * Bt + L->row0);
-      b.p[d].seg[1].a_c1 = (int)(t * Bt + L->row0);
+      b.p[d].seg[0].x_c1 = (int)(t * Bt + L->row0);
+      b.p[d].seg[1].x_c1 = (int)(t * Bt + L->row0);
       fill_epi(b.p[d].epi, d, s);
     }
     IPN_PROPAGATE((launch_umma<Cfg, EpiGruBwd>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));

@@ -33,30 +33,31 @@ inline void fill_simt_seg(SimtSeg& s, const HostOperand& a, const HostOperand& b
   s.K = K;
 }
 
-// box_rows_b: rows per TMA box of a K-major B operand (= BNG of the kernel config)
-inline int fill_umma_seg(UmmaSeg& s, const HostOperand& a, const HostOperand& b, int K, int box_rows_b) {
+// x = activation-side operand (output rows), w = weight-side operand (output columns / TMEM lanes).
+// box_rows_x: rows per TMA box of a K-major X operand (= BR of the kernel config)
+inline int fill_umma_seg(UmmaSeg& s, const HostOperand& x, const HostOperand& w, int K, int box_rows_x) {
   s.K = K;
-  if (!a.trans) {
-    IPN_PROPAGATE(get_tensor_map(&s.tmA, a.ptr, (unsigned long long)(a.k_off + K), (unsigned long long)a.rows_total,
-                                 a.ld, UMMA_BM));
-    s.a_c0 = (int)a.k_off;
-    s.a_c1 = (int)a.row_off;
+  if (!w.trans) {
+    IPN_PROPAGATE(get_tensor_map(&s.tmW, w.ptr, (unsigned long long)(w.k_off + K), (unsigned long long)w.rows_total,
+                                 w.ld, UMMA_BC));
+    s.w_c0 = (int)w.k_off;
+    s.w_c1 = (int)w.row_off;
   } else {
-    IPN_PROPAGATE(get_tensor_map(&s.tmA, a.ptr, (unsigned long long)a.rows_total, (unsigned long long)(a.k_off + K),
-                                 a.ld, 64));
-    s.a_c0 = (int)a.row_off;
-    s.a_c1 = (int)a.k_off;
+    IPN_PROPAGATE(get_tensor_map(&s.tmW, w.ptr, (unsigned long long)w.rows_total, (unsigned long long)(w.k_off + K),
+                                 w.ld, 64));
+    s.w_c0 = (int)w.row_off;
+    s.w_c1 = (int)w.k_off;
   }
-  if (!b.trans) {
-    IPN_PROPAGATE(get_tensor_map(&s.tmB, b.ptr, (unsigned long long)(b.k_off + K), (unsigned long long)b.rows_total,
-                                 b.ld, (unsigned)box_rows_b));
-    s.b_c0 = (int)b.k_off;
-    s.b_c1 = (int)b.row_off;
+  if (!x.trans) {
+    IPN_PROPAGATE(get_tensor_map(&s.tmX, x.ptr, (unsigned long long)(x.k_off + K), (unsigned long long)x.rows_total,
+                                 x.ld, (unsigned)box_rows_x));
+    s.x_c0 = (int)x.k_off;
+    s.x_c1 = (int)x.row_off;
   } else {
-    IPN_PROPAGATE(get_tensor_map(&s.tmB, b.ptr, (unsigned long long)b.rows_total, (unsigned long long)(b.k_off + K),
-                                 b.ld, 64));
-    s.b_c0 = (int)b.row_off;
-    s.b_c1 = (int)b.k_off;
+    IPN_PROPAGATE(get_tensor_map(&s.tmX, x.ptr, (unsigned long long)x.rows_total, (unsigned long long)(x.k_off + K),
+                                 x.ld, 64));
+    s.x_c0 = (int)x.row_off;
+    s.x_c1 = (int)x.k_off;
   }
   return IPN_OK;
 }
@@ -82,7 +83,8 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
     IPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(cdiv(maxN, Cfg::BNG), cdiv(maxM, UMMA_BM), nprob * batch.split_k);
+  dim3 grid(cdiv(maxN, UMMA_BC), cdiv(maxM, Cfg::BR), nprob * batch.split_k);
+  IPN_REQUIRE(grid.y <= 65535, IPN_ERR_ARG, "too many row tiles (%u) for one launch", grid.y);
   kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(batch);
   IPN_LAUNCH_CHECK();
   return IPN_OK;

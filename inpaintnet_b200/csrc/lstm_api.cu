@@ -5,15 +5,15 @@ namespace ipn {
 
 template <int W>
 __global__ void lstm_bwd_point_kernel(LstmBwdPoint p, int nrows) {
-  const int chunks = (p.H + W - 1) / W;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nrows * chunks) return;
-  const int row = (int)(idx / chunks);
-  const int col0 = (int)(idx % chunks) * W;
+  const int rchunks = (nrows + W - 1) / W;
+  if (idx >= (long long)rchunks * p.H) return;
+  const int col = (int)(idx % p.H);
+  const int row0 = (int)(idx / p.H) * W;
   float dh[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) dh[i] = 0.f;
-  lstm_bwd_pointwise<W>(p, row, col0, min(W, p.H - col0), dh);
+  lstm_bwd_pointwise<W>(p, col, row0, min(W, nrows - row0), dh);
 }
 
 static int check_lstm(int core, int act_dt, int T, int B, int H) {
@@ -60,7 +60,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
     }
     return IPN_OK;
   }
-  using Cfg = UmmaCfg<4, 64, false, false>;
+  using Cfg = UmmaCfg<4, 64, false, false, 200>;   // 128 units x 64 rows x 4 gates: 256 TMEM columns
   UmmaBatch<EpiLstmFwd> b;
   memset(&b, 0, sizeof(b));
   b.split_k = 1;
@@ -68,9 +68,9 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = H;
   HostOperand a{L->hseq, H, 0, (T + 1) * B, 0, 0};
   HostOperand w{L->w_hh, H, 0, 4LL * H, 0, 0};
-  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BNG));
+  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BR));
   for (int s = 0; s < T; ++s) {
-    P.seg[0].a_c1 = (int)(s * B);
+    P.seg[0].x_c1 = (int)(s * B);
     fill_epi(P.epi, s);
     IPN_PROPAGATE((launch_umma<Cfg, EpiLstmFwd>(b, 1, (int)B, H, stream, "lstm_step_fwd_umma")));
   }
@@ -99,7 +99,7 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
     LstmBwdPoint p;
     fill_point(p, T - 1);
     constexpr int W = 4;
-    const long long work = B * ((H + W - 1) / W);
+    const long long work = ((B + W - 1) / W) * H;
     lstm_bwd_point_kernel<W><<<cdiv(work, 256), 256, 0, stream>>>(p, (int)B);
     IPN_LAUNCH_CHECK();
   }
@@ -119,7 +119,7 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
     }
     return IPN_OK;
   }
-  using Cfg = UmmaCfg<1, 128, false, true>;
+  using Cfg = UmmaCfg<1, 128, true, false>;
   UmmaBatch<EpiLstmBwd> b;
   memset(&b, 0, sizeof(b));
   b.split_k = 1;
@@ -127,9 +127,9 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
   P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = 0;
   HostOperand a{L->dP, 4LL * H, 0, T * B, 0, 0};
   HostOperand w{L->w_hh, H, 1, H, 0, 0};
-  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, 4 * H, Cfg::BNG));
+  IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, 4 * H, Cfg::BR));
   for (int s = T - 1; s >= 1; --s) {
-    P.seg[0].a_c1 = (int)(s * B);
+    P.seg[0].x_c1 = (int)(s * B);
     P.epi.is_first_step = 0;
     fill_point(P.epi.pw, s - 1);
     IPN_PROPAGATE((launch_umma<Cfg, EpiLstmBwd>(b, 1, (int)B, H, stream, "lstm_step_bwd_umma")));
