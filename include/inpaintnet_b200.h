@@ -71,6 +71,9 @@ long long ipn_launch_count(void);
  * roofline numbers; off by default).  ipn_prof_report synchronises the device and writes one line per
  * kernel class: tag \t launches \t total_ms \t algorithmic_flops \t algorithmic_bytes. */
 void ipn_prof_enable(int on);
+/* diagnostics: when non-null, every CTA of the GRU forward step kernel writes 8 globaltimer stamps
+ * (start, setup done, TMA issued, MMA issued, accumulators ready, first epilogue warp done, all done, -) */
+void ipn_dbg_set_timing_buffer(void* dev_ptr);
 int ipn_prof_report(char* buf_host, int cap);
 
 /* 3-level affine row map: off = (r / g1) * s1 + ((r % g1) / g2) * s2 + (r % g2) * s3 (elements) */

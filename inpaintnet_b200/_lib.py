@@ -95,6 +95,7 @@ SYMBOLS = {
     "ipn_device_check": (i32, [i32, C.POINTER(i32)]),
     "ipn_launch_count": (ll, []),
     "ipn_prof_enable": (None, [i32]),
+    "ipn_dbg_set_timing_buffer": (None, [vp]),
     "ipn_prof_report": (i32, [C.c_char_p, i32]),
     "ipn_gemm": (i32, [C.POINTER(Gemm), vp]),
     "ipn_gru_layer_fwd": (i32, [C.POINTER(GruLayer), vp]),

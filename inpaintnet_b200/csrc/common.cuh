@@ -159,6 +159,38 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// compile-time dtype variants (DT = IPN_BF16 / IPN_F32, or -1 = decide at run time from `rt`).  With a
+// compile-time dtype there is no branch between a load and its conversion, so the compiler can issue all
+// loads of an epilogue phase back to back (memory-level parallelism) instead of serialising them.
+template <int DT>
+__device__ __forceinline__ float ld_t(const void* p, long long i, int rt) {
+  if constexpr (DT == IPN_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  else if constexpr (DT == IPN_F32) return reinterpret_cast<const float*>(p)[i];
+  else return ld_act(p, i, rt);
+}
+template <int DT>
+__device__ __forceinline__ void st_t(void* p, long long i, float v, int rt) {
+  if constexpr (DT == IPN_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else if constexpr (DT == IPN_F32) reinterpret_cast<float*>(p)[i] = v;
+  else st_act(p, i, v, rt);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16 mode: one MUFU op per gate (outputs are rounded to bf16 anyway); fp32 mode: accurate libm paths
+template <int DT>
+__device__ __forceinline__ float sigmoid_t(float x) {
+  if constexpr (DT == IPN_BF16) return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
+  else return sigmoid_acc(x);
+}
+template <int DT>
+__device__ __forceinline__ float tanh_t(float x) {
+  if constexpr (DT == IPN_BF16) return tanh_approx(x);
+  else return tanhf(x);
+}
+
 // 3-level affine row map: off = (r / g1) * s1 + ((r % g1) / g2) * s2 + (r % g2) * s3
 __device__ __forceinline__ long long map_row(const IpnRowMap& m, int r) {
   const int a = r / m.g1, rem = r - a * m.g1;

@@ -17,6 +17,8 @@ namespace ipn {
 // Linear: out = alpha * act(acc + bias) * mul     (+ row map, column split, accumulate modes)
 // =============================================================================================
 struct EpiLinear {
+  template <class PP>
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const PP&) { return nullptr; }
   static constexpr int G = 1;
   struct Params {
     void* out;
@@ -51,43 +53,80 @@ struct EpiLinear {
       cc.base += q * p.split_stride * (p.out_dt == IPN_BF16 ? 2 : 4);
     }
   }
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  template <int W> struct Pre {};
+  template <int W>
+  static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[G][W], const Pre<W>&) { applyT<W>(p, cc, col, row0, nv, acc); }
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
                                                 float (&acc)[1][W]) {
+    // offsets first (one hoisted branch), then all loads, then math + stores; rows beyond nv are clamped
+    long long off[W];
+    if (p.use_rowmap) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) off[i] = map_row(p.rowmap, row0 + min(i, nv - 1)) + cc.c;
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) off[i] = (long long)(row0 + min(i, nv - 1)) * p.ld_out + cc.c;
+    }
     float m[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) m[i] = 1.f;
-    if (p.mul_mode != IPN_MUL_NONE) {
+    for (int i = 0; i < W; ++i) m[i] = p.alpha;
+    if (p.mul_mode == IPN_MUL_KEEP_MASK) {
+      unsigned char mb[W];
 #pragma unroll
-      for (int i = 0; i < W; ++i) {
-        if (i < nv) {
-          const long long mo = (long long)(row0 + i) * p.ld_mul + col;
-          if (p.mul_mode == IPN_MUL_KEEP_MASK) {
-            m[i] = reinterpret_cast<const unsigned char*>(p.mul_src)[mo] ? p.mul_scale : 0.f;
-          } else {
-            const float y = ld_act(p.mul_src, mo, p.mul_dt);
-            m[i] = (p.mul_mode == IPN_MUL_SELU_GRAD) ? selu_grad_from_out(y) : (y > 0.f ? 1.f : 0.f);
-          }
-        }
+      for (int i = 0; i < W; ++i)
+        mb[i] = reinterpret_cast<const unsigned char*>(p.mul_src)[(long long)(row0 + min(i, nv - 1)) * p.ld_mul + col];
+#pragma unroll
+      for (int i = 0; i < W; ++i) m[i] = mb[i] ? p.alpha * p.mul_scale : 0.f;
+    } else if (p.mul_mode != IPN_MUL_NONE) {
+      float y[W];
+      if (p.mul_dt == IPN_BF16) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) y[i] = ld_t<IPN_BF16>(p.mul_src, (long long)(row0 + min(i, nv - 1)) * p.ld_mul + col, 0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) y[i] = ld_t<IPN_F32>(p.mul_src, (long long)(row0 + min(i, nv - 1)) * p.ld_mul + col, 0);
       }
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        m[i] *= (p.mul_mode == IPN_MUL_SELU_GRAD) ? selu_grad_from_out(y[i]) : (y[i] > 0.f ? 1.f : 0.f);
     }
-    long long off[W];
+    float v[W];
+    if (p.act == IPN_ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < W; ++i)
-      off[i] = (p.use_rowmap ? map_row(p.rowmap, row0 + i) : (long long)(row0 + i) * p.ld_out) + cc.c;
-    float old[W];
-    if (p.accumulate == IPN_RMW_ADD) {
+      for (int i = 0; i < W; ++i) v[i] = (acc[0][i] + cc.bias) * m[i];
+    } else if (p.act == IPN_ACT_RELU) {
 #pragma unroll
-      for (int i = 0; i < W; ++i) old[i] = (i < nv) ? ld_act(cc.base, off[i], p.out_dt) : 0.f;
+      for (int i = 0; i < W; ++i) v[i] = fmaxf(acc[0][i] + cc.bias, 0.f) * m[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] = selu_f(acc[0][i] + cc.bias) * m[i];
     }
+    if (p.accumulate == IPN_STORE) {
+      if (p.out_dt == IPN_BF16) {
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      if (i < nv) {
-        const float v = apply_act(acc[0][i] + cc.bias, p.act) * p.alpha * m[i];
-        if (p.accumulate == IPN_STORE) st_act(cc.base, off[i], v, p.out_dt);
-        else if (p.accumulate == IPN_ATOMIC_ADD) atomicAdd(reinterpret_cast<float*>(cc.base) + off[i], v);
-        else st_act(cc.base, off[i], old[i] + v, p.out_dt);
+        for (int i = 0; i < W; ++i)
+          if (i < nv) st_t<IPN_BF16>(cc.base, off[i], v[i], 0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+          if (i < nv) st_t<IPN_F32>(cc.base, off[i], v[i], 0);
       }
+    } else if (p.accumulate == IPN_ATOMIC_ADD) {
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (i < nv) atomicAdd(reinterpret_cast<float*>(cc.base) + off[i], v[i]);
+    } else {
+      float old[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) old[i] = ld_act(cc.base, off[i], p.out_dt);
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (i < nv) st_act(cc.base, off[i], old[i] + v[i], p.out_dt);
     }
   }
 };
@@ -95,9 +134,7 @@ struct EpiLinear {
 // =============================================================================================
 // GRU forward step:  acc[g] = (h_prev W_hh^T)[row, g*H + col]   g in {r, z, n}
 // =============================================================================================
-struct EpiGruFwd {
-  static constexpr int G = 3;
-  struct Params {
+struct GruFwdParams {
     int H, act_dt, row0;
     long long trow;  // t * B_total: first row of this timestep in time-ordered buffers
     const void* P;
@@ -121,7 +158,16 @@ struct EpiGruFwd {
     int final_dt;
     long long ld_final;
     int final_col0;
-  };
+    int dbg;  // diagnostics (IPN_DBG_EPI): bit0 skip loads, bit1 skip stores
+    unsigned long long* dbg_buf;  // per-CTA phase timestamps (IPN_DBG_TIMING), normally null
+  __device__ __forceinline__ float mask_scale_eff() const { return mask != nullptr ? mask_scale : 1.f; }
+};
+
+template <int DT>
+struct EpiGruFwdT {
+  static constexpr int G = 3;
+  using Params = GruFwdParams;
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const Params& p) { return p.dbg_buf; }
   struct Col {
     float br, bz, bn;  // b_hh
     float cr, cz, cn;  // constant part of the input projection (pvec)
@@ -132,51 +178,103 @@ struct EpiGruFwd {
     cc.cr = cc.cz = cc.cn = 0.f;
     if (p.pvec != nullptr) { cc.cr = p.pvec[col]; cc.cz = p.pvec[H + col]; cc.cn = p.pvec[2 * H + col]; }
   }
+  // Load phase, separated from the math so that the tcgen05 kernel can issue the loads of the NEXT 8-row
+  // phase before finishing the current one (software pipelining) and the first phase before the
+  // accumulators are even ready.  All loads of the W rows are issued array by array with no consumer in
+  // between; rows beyond nv re-read the last valid row instead of branching.
+  template <int W>
+  struct Pre {
+    float pr[W], pz[W], pn[W], hp[W];
+    unsigned mask_bits;
+  };
+  template <int W>
+  static __device__ __forceinline__ void preload(const Params& p, const Col& cc, int col, int row0, int nv, Pre<W>& q) {
+    const int H = p.H, dt = p.act_dt;
+    long long R[W], TR[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      R[i] = p.row0 + row0 + min(i, nv - 1);
+      TR[i] = p.trow + R[i];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { q.pr[i] = cc.cr; q.pz[i] = cc.cz; q.pn[i] = cc.cn; }
+    q.mask_bits = 0xffffffffu;
+    const bool ld_on = !(p.dbg & 1);
+    float a[W], b[W], c[W];
+    if (p.P != nullptr && ld_on) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const long long o = (p.P_bcast ? R[i] : TR[i]) * p.ldP + col;
+        a[i] = ld_t<DT>(p.P, o, dt); b[i] = ld_t<DT>(p.P, o + H, dt); c[i] = ld_t<DT>(p.P, o + 2 * H, dt);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) { a[i] = 0.f; b[i] = 0.f; c[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) q.hp[i] = ld_on ? ld_t<DT>(p.h_prev, R[i] * H + col, dt) : 0.f;
+    unsigned char mb[W];
+    const bool has_mask = p.y != nullptr && p.mask != nullptr && ld_on;
+    if (has_mask) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) mb[i] = p.mask[TR[i] * p.ld_mask + p.y_col0 + col];
+    }
+    if (p.table != nullptr && ld_on) {
+      int tk[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) tk[i] = p.tok[TR[i]];
+      float tr[W], tz[W], tn[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const long long o = (long long)tk[i] * p.ld_table + col;
+        tr[i] = p.table[o]; tz[i] = p.table[o + H]; tn[i] = p.table[o + 2 * H];
+      }
+#pragma unroll
+      for (int i = 0; i < W; ++i) { q.pr[i] += tr[i]; q.pz[i] += tz[i]; q.pn[i] += tn[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { q.pr[i] += a[i]; q.pz[i] += b[i]; q.pn[i] += c[i]; }
+    if (has_mask) {
+      unsigned bits = 0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) bits |= (mb[i] ? 1u : 0u) << i;
+      q.mask_bits = bits;
+    }
+  }
+  // gate math + stores
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
-                                                float (&acc)[3][W]) {
+                                                float (&acc)[3][W], const Pre<W>& q) {
     const int H = p.H, dt = p.act_dt;
-    float pr[W], pz[W], pn[W], hp[W], mk[W];
-    // ---- phase 1: all loads
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      pr[i] = cc.cr; pz[i] = cc.cz; pn[i] = cc.cn; hp[i] = 0.f; mk[i] = 1.f;
-      if (i < nv) {
+      const float r = sigmoid_t<DT>(q.pr[i] + acc[0][i] + cc.br);
+      const float z = sigmoid_t<DT>(q.pz[i] + acc[1][i] + cc.bz);
+      const float hn = acc[2][i] + cc.bn;
+      const float n = tanh_t<DT>(q.pn[i] + r * hn);
+      const float h = (1.f - z) * n + z * q.hp[i];
+      if (i < nv && !(p.dbg & 2)) {
         const long long R = p.row0 + row0 + i, TR = p.trow + R;
-        if (p.P != nullptr) {
-          const long long o = (p.P_bcast ? R : TR) * p.ldP + col;
-          pr[i] += ld_act(p.P, o, dt); pz[i] += ld_act(p.P, o + H, dt); pn[i] += ld_act(p.P, o + 2 * H, dt);
-        }
-        if (p.table != nullptr) {
-          const long long o = (long long)p.tok[TR] * p.ld_table + col;
-          pr[i] += p.table[o]; pz[i] += p.table[o + H]; pn[i] += p.table[o + 2 * H];
-        }
-        hp[i] = ld_act(p.h_prev, R * H + col, dt);
-        if (p.y != nullptr && p.mask != nullptr) mk[i] = p.mask[TR * p.ld_mask + p.y_col0 + col] ? p.mask_scale : 0.f;
-      }
-    }
-    // ---- phase 2: gate math + stores
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      if (i < nv) {
-        const long long R = p.row0 + row0 + i, TR = p.trow + R;
-        const float r = sigmoid_acc(pr[i] + acc[0][i] + cc.br);
-        const float z = sigmoid_acc(pz[i] + acc[1][i] + cc.bz);
-        const float hn = acc[2][i] + cc.bn;
-        const float n = tanhf(pn[i] + r * hn);
-        const float h = (1.f - z) * n + z * hp[i];
-        st_act(p.h_out, R * H + col, h, dt);
+        st_t<DT>(p.h_out, R * H + col, h, dt);
         if (p.gates != nullptr) {
           const long long go = TR * 4 * H + col;
-          st_act(p.gates, go, r, dt); st_act(p.gates, go + H, z, dt);
-          st_act(p.gates, go + 2 * H, n, dt); st_act(p.gates, go + 3 * H, hn, dt);
+          st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
+          st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
         }
-        if (p.y != nullptr) st_act(p.y, TR * p.ld_y + p.y_col0 + col, h * mk[i], dt);
+        if (p.y != nullptr) st_t<DT>(p.y, TR * p.ld_y + p.y_col0 + col, ((q.mask_bits >> i) & 1u) ? h * p.mask_scale_eff() : 0.f, dt);
         if (p.final_out != nullptr) st_act(p.final_out, R * p.ld_final + p.final_col0 + col, h, p.final_dt);
       }
     }
   }
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[3][W]) {
+    Pre<W> q;
+    preload<W>(p, cc, col, row0, nv, q);
+    applyT<W>(p, cc, col, row0, nv, acc, q);
+  }
 };
+using EpiGruFwd = EpiGruFwdT<-1>;
 
 // =============================================================================================
 // GRU backward.  Pointwise part for one timestep (shared by the GEMM epilogue and the standalone
@@ -200,49 +298,63 @@ struct GruBwdPoint {
   float* dhz_out;       // [B_total, H] fp32: dh * z for the next (earlier) step
 };
 
-template <int W>
+template <int DT, int W>
 __device__ __forceinline__ void gru_bwd_pointwise(const GruBwdPoint& p, int col, int row0, int nv,
                                                   const float (&dh_in)[W]) {
   const int H = p.H, dt = p.act_dt;
-  float dh[W], r[W], z[W], n[W], hn[W], hp[W];
+  long long R[W], TR[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    dh[i] = dh_in[i]; r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
-    if (i < nv) {
-      const long long R = p.row0 + row0 + i, TR = p.trow + R;
-      if (p.dY != nullptr) {
-        float dy = ld_act(p.dY, TR * p.ld_dy + p.y_col0 + col, dt);
-        if (p.mask != nullptr) dy = p.mask[TR * p.ld_mask + p.y_col0 + col] ? dy * p.mask_scale : 0.f;
-        dh[i] += dy;
-      }
-      if (p.dh_n != nullptr) dh[i] += p.dh_n[R * p.ld_dhn + col];
-      const long long go = TR * 4 * H + col;
-      r[i] = ld_act(p.gates, go, dt); z[i] = ld_act(p.gates, go + H, dt);
-      n[i] = ld_act(p.gates, go + 2 * H, dt); hn[i] = ld_act(p.gates, go + 3 * H, dt);
-      hp[i] = ld_act(p.h_prev, R * H + col, dt);
-    }
+    R[i] = p.row0 + row0 + min(i, nv - 1);
+    TR[i] = p.trow + R[i];
+  }
+  // ---- phase 1: all loads, array by array (see EpiGruFwdT)
+  float r[W], z[W], n[W], hn[W], hp[W], dy[W], dn_[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const long long go = TR[i] * 4 * H + col;
+    r[i] = ld_t<DT>(p.gates, go, dt); z[i] = ld_t<DT>(p.gates, go + H, dt);
+    n[i] = ld_t<DT>(p.gates, go + 2 * H, dt); hn[i] = ld_t<DT>(p.gates, go + 3 * H, dt);
   }
 #pragma unroll
+  for (int i = 0; i < W; ++i) hp[i] = ld_t<DT>(p.h_prev, R[i] * H + col, dt);
+#pragma unroll
+  for (int i = 0; i < W; ++i) { dy[i] = 0.f; dn_[i] = 0.f; }
+  if (p.dY != nullptr) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) dy[i] = ld_t<DT>(p.dY, TR[i] * p.ld_dy + p.y_col0 + col, dt);
+    if (p.mask != nullptr) {
+      unsigned char mb[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) mb[i] = p.mask[TR[i] * p.ld_mask + p.y_col0 + col];
+#pragma unroll
+      for (int i = 0; i < W; ++i) dy[i] = mb[i] ? dy[i] * p.mask_scale : 0.f;
+    }
+  }
+  if (p.dh_n != nullptr) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) dn_[i] = p.dh_n[R[i] * p.ld_dhn + col];
+  }
+  // ---- phase 2
+#pragma unroll
   for (int i = 0; i < W; ++i) {
+    const float dh = dh_in[i] + dy[i] + dn_[i];
+    const float dn = dh * (1.f - z[i]) * (1.f - n[i] * n[i]);
+    const float dz = dh * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
+    const float dr = dn * hn[i] * r[i] * (1.f - r[i]);
     if (i < nv) {
-      const long long R = p.row0 + row0 + i, TR = p.trow + R;
-      const float dn = dh[i] * (1.f - z[i]) * (1.f - n[i] * n[i]);
-      const float dz = dh[i] * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
-      const float dr = dn * hn[i] * r[i] * (1.f - r[i]);
-      st_act(p.dP, TR * 3 * H + col, dr, dt);
-      st_act(p.dP, TR * 3 * H + H + col, dz, dt);
-      st_act(p.dP, TR * 3 * H + 2 * H + col, dn, dt);
-      st_act(p.dGn, TR * H + col, dn * r[i], dt);
-      p.dhz_out[R * H + col] = dh[i] * z[i];
+      st_t<DT>(p.dP, TR[i] * 3 * H + col, dr, dt);
+      st_t<DT>(p.dP, TR[i] * 3 * H + H + col, dz, dt);
+      st_t<DT>(p.dP, TR[i] * 3 * H + 2 * H + col, dn, dt);
+      st_t<DT>(p.dGn, TR[i] * H + col, dn * r[i], dt);
+      p.dhz_out[R[i] * H + col] = dh * z[i];
     }
   }
 }
 
 // GEMM epilogue: acc = ([dP_r, dP_z | dGn] W_hh)[row, col] of step s  ->  dh wrt the state that entered
 // step s; then either emit dh0 (first step of the chain) or differentiate the previous step's gates.
-struct EpiGruBwd {
-  static constexpr int G = 1;
-  struct Params {
+struct GruBwdParams {
     const float* dhz_in;  // [B_total, H] fp32, nullable
     int is_first_step;    // this GEMM produced the gradient wrt h0
     void* dh0;
@@ -251,18 +363,36 @@ struct EpiGruBwd {
     int dh0_selu;
     const void* h0;  // slot base of h0 (act_dt), for SELU'
     GruBwdPoint pw;  // describes step s-1 (unused when is_first_step)
-  };
+};
+
+template <int DT>
+struct EpiGruBwdT {
+  template <class PP>
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const PP&) { return nullptr; }
+  static constexpr int G = 1;
+  using Params = GruBwdParams;
   struct Col {};
   static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  template <int W> struct Pre {};
+  template <int W>
+  static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[G][W], const Pre<W>&) { applyT<W>(p, cc, col, row0, nv, acc); }
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col&, int col, int row0, int nv,
                                                 float (&acc)[1][W]) {
     const int H = p.pw.H;
     float dh[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      dh[i] = acc[0][i];
-      if (p.dhz_in != nullptr && i < nv) dh[i] += p.dhz_in[(long long)(p.pw.row0 + row0 + i) * H + col];
+    for (int i = 0; i < W; ++i) dh[i] = acc[0][i];
+    if (p.dhz_in != nullptr) {
+      float t[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) t[i] = p.dhz_in[(long long)(p.pw.row0 + row0 + min(i, nv - 1)) * H + col];
+#pragma unroll
+      for (int i = 0; i < W; ++i) dh[i] += t[i];
     }
     if (p.is_first_step) {
       if (p.dh0 != nullptr) {
@@ -271,21 +401,24 @@ struct EpiGruBwd {
           if (i < nv) {
             const long long R = p.pw.row0 + row0 + i;
             float v = dh[i];
-            if (p.dh0_selu) v *= selu_grad_from_out(ld_act(p.h0, R * H + col, p.pw.act_dt));
+            if (p.dh0_selu) v *= selu_grad_from_out(ld_t<DT>(p.h0, R * H + col, p.pw.act_dt));
             st_act(p.dh0, R * p.ld_dh0 + col, v, p.dh0_dt);
           }
         }
       }
       return;
     }
-    gru_bwd_pointwise<W>(p.pw, col, row0, nv, dh);
+    gru_bwd_pointwise<DT, W>(p.pw, col, row0, nv, dh);
   }
 };
+using EpiGruBwd = EpiGruBwdT<-1>;
 
 // =============================================================================================
 // LSTM forward step: acc[g] = (h_prev W_hh^T)[row, g*H + col], g in {i, f, g, o}
 // =============================================================================================
 struct EpiLstmFwd {
+  template <class PP>
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const PP&) { return nullptr; }
   static constexpr int G = 4;
   struct Params {
     int H, act_dt;
@@ -308,6 +441,13 @@ struct EpiLstmFwd {
 #pragma unroll
     for (int g = 0; g < 4; ++g) cc.b[g] = p.b_hh != nullptr ? p.b_hh[g * p.H + col] : 0.f;
   }
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  template <int W> struct Pre {};
+  template <int W>
+  static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[G][W], const Pre<W>&) { applyT<W>(p, cc, col, row0, nv, acc); }
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
                                                 float (&acc)[4][W]) {
@@ -400,6 +540,8 @@ __device__ __forceinline__ void lstm_bwd_pointwise(const LstmBwdPoint& p, int co
 
 // GEMM epilogue: acc = (dP[s] W_hh)[row, col] = gradient wrt h_{s-1} from the recurrence.
 struct EpiLstmBwd {
+  template <class PP>
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const PP&) { return nullptr; }
   static constexpr int G = 1;
   struct Params {
     int is_first_step;  // nothing earlier to differentiate
@@ -407,6 +549,13 @@ struct EpiLstmBwd {
   };
   struct Col {};
   static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  template <int W> struct Pre {};
+  template <int W>
+  static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
+                                                float (&acc)[G][W], const Pre<W>&) { applyT<W>(p, cc, col, row0, nv, acc); }
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col&, int col, int row0, int nv,
                                                 float (&acc)[1][W]) {

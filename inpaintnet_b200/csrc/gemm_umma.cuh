@@ -69,6 +69,22 @@ struct UmmaCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "stage configuration exceeds shared memory");
 };
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// optional per-CTA phase timestamps (diagnostics): Epi::dbg_buf(params) returns a device buffer or nullptr
+template <class Epi>
+__device__ __forceinline__ void dbg_stamp(const typename Epi::Params& p, int slot) {
+  unsigned long long* buf = Epi::dbg_buf(p);
+  if (buf != nullptr) {
+    const long long cta = (long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    buf[cta * 8 + slot] = gtimer();
+  }
+}
+
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(UMMA_THREADS, Cfg::CTAS_PER_SM)
 umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
@@ -97,6 +113,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   const int kc_end = min(chunks_total, kc_begin + per);
   const int nchunks = kc_end - kc_begin;
 
+  if (threadIdx.x == 0) dbg_stamp<Epi>(P.epi, 0);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
@@ -121,6 +138,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) dbg_stamp<Epi>(P.epi, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -155,6 +173,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      dbg_stamp<Epi>(P.epi, 2);  // all TMA loads issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -182,6 +201,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       ptx::umma_commit(tmem_full_bar);
+      dbg_stamp<Epi>(P.epi, 3);  // all MMAs issued
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -195,6 +215,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
+    if (threadIdx.x == 64) dbg_stamp<Epi>(P.epi, 4);  // accumulators complete
 #pragma unroll 1
     for (int c = half; c < BR / 16; c += 2) {
       const int row0 = r0 + c * 16;
@@ -213,7 +234,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
       }
       if (col_ok) {
         const int nv = min(16, P.M - row0);
-        // two halves of 8 rows: bounds the registers held by the epilogue's load phase
+        // two phases of 8 rows (bounds the registers held by an epilogue's load phase).  Issuing the next
+        // phase's loads early (register double buffering) was measured slower: it spills.
         float a8[G][8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -227,8 +249,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
       }
     }
   }
+  if (threadIdx.x == 64) dbg_stamp<Epi>(P.epi, 5);  // first epilogue warp done
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) dbg_stamp<Epi>(P.epi, 6);  // all warps done
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

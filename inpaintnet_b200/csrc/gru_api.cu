@@ -1,6 +1,7 @@
 // GRU layer forward / backward drivers: one fused kernel per timestep (recurrent GEMM + gate math
 // in the epilogue), all directions of the layer in the same launch.
 #include "launch.cuh"
+#include <stdlib.h>
 
 namespace ipn {
 
@@ -16,7 +17,7 @@ __global__ void gru_bwd_point_kernel(GruBwdPoint p0, GruBwdPoint p1, int nrows) 
   float dh[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) dh[i] = 0.f;
-  gru_bwd_pointwise<W>(p, col, row0, min(W, nrows - row0), dh);
+  gru_bwd_pointwise<-1, W>(p, col, row0, min(W, nrows - row0), dh);
 }
 
 static inline const char* slot_ptr(const void* base, long long slot, long long B_total, int H, int dt) {
@@ -38,6 +39,9 @@ static int check_layer_common(int core, int act_dt, int T, int B_total, int H, i
 
 using namespace ipn;
 
+static unsigned long long* g_dbg_timing = nullptr;
+extern "C" void ipn_dbg_set_timing_buffer(void* dev_ptr) { g_dbg_timing = reinterpret_cast<unsigned long long*>(dev_ptr); }
+
 extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "gru_layer_fwd: null descriptor");
@@ -53,7 +57,9 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     IPN_REQUIRE(!D.table || D.tok, IPN_ERR_ARG, "gru_layer_fwd: table without tokens");
   }
 
-  auto fill_epi = [&](EpiGruFwd::Params& e, const IpnGruDir& D, int s) {
+  static const int dbg_epi = getenv("IPN_DBG_EPI") ? atoi(getenv("IPN_DBG_EPI")) : 0;
+  static const int gru_br = getenv("IPN_GRU_BR") ? atoi(getenv("IPN_GRU_BR")) : 128;
+  auto fill_epi = [&](GruFwdParams& e, const IpnGruDir& D, int s) {
     const int t = D.reverse ? T - 1 - s : s;
     const int in_slot = D.reverse ? t + 1 : t, out_slot = D.reverse ? t : t + 1;
     e.H = H; e.act_dt = dt; e.row0 = L->row0; e.trow = (long long)t * Bt;
@@ -73,6 +79,8 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
       e.final_dt = L->final_dt; e.ld_final = L->ld_final;
     }
     e.final_col0 = D.final_col0;
+    e.dbg = dbg_epi;
+    e.dbg_buf = g_dbg_timing;
     return in_slot;
   };
 
@@ -95,26 +103,33 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     return IPN_OK;
   }
 
-  using Cfg = UmmaCfg<3, 128, false, false, 200>;   // 128 units x 128 rows x 3 gates: 384 TMEM columns, 1 CTA/SM
-  UmmaBatch<EpiGruFwd> b;
-  memset(&b, 0, sizeof(b));
-  b.split_k = 1;
-  for (int d = 0; d < L->ndir; ++d) {
-    const IpnGruDir& D = L->dir[d];
-    UmmaProblem<EpiGruFwd>& P = b.p[d];
-    P.nseg = 1; P.M = L->nrows; P.N = H; P.gate_stride = H;
-    HostOperand a{D.hseq, H, 0, (long long)(T + 1) * Bt, 0, 0};
-    HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BR));
-  }
-  for (int s = L->s_begin; s < L->s_end; ++s) {
+  auto run = [&](auto cfg_tag) -> int {
+    using Cfg = decltype(cfg_tag);
+    using Epi = EpiGruFwdT<IPN_BF16>;
+    UmmaBatch<Epi> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
     for (int d = 0; d < L->ndir; ++d) {
-      const int in_slot = fill_epi(b.p[d].epi, L->dir[d], s);
-      b.p[d].seg[0].x_c1 = (int)(in_slot * Bt + L->row0);
+      const IpnGruDir& D = L->dir[d];
+      UmmaProblem<Epi>& P = b.p[d];
+      P.nseg = 1; P.M = L->nrows; P.N = H; P.gate_stride = H;
+      HostOperand a{D.hseq, H, 0, (long long)(T + 1) * Bt, 0, 0};
+      HostOperand w{D.w_hh, H, 0, 3LL * H, 0, 0};
+      IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BR));
     }
-    IPN_PROPAGATE((launch_umma<Cfg, EpiGruFwd>(b, L->ndir, L->nrows, H, stream, "gru_step_fwd_umma")));
-  }
-  return IPN_OK;
+    for (int s = L->s_begin; s < L->s_end; ++s) {
+      for (int d = 0; d < L->ndir; ++d) {
+        const int in_slot = fill_epi(b.p[d].epi, L->dir[d], s);
+        b.p[d].seg[0].x_c1 = (int)(in_slot * Bt + L->row0);
+      }
+      IPN_PROPAGATE((launch_umma<Cfg, Epi>(b, L->ndir, L->nrows, H, stream, "gru_step_fwd_umma")));
+    }
+    return IPN_OK;
+  };
+  // 128 hidden units x BR rows x 3 gates per CTA
+  if (gru_br == 64) return run(UmmaCfg<3, 64, false, false, 112>{});    // 192 TMEM columns, 2 CTAs/SM
+  if (gru_br == 32) return run(UmmaCfg<3, 32, false, false, 112>{});    // 96 TMEM columns, 2 CTAs/SM
+  return run(UmmaCfg<3, 128, false, false, 200>{});                     // 384 TMEM columns, 1 CTA/SM
 }
 
 extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
@@ -160,7 +175,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     IPN_LAUNCH_CHECK();
   }
 
-  auto fill_epi = [&](EpiGruBwd::Params& e, int d, int s) {
+  auto fill_epi = [&](GruBwdParams& e, int d, int s) {
     const IpnGruBwdDir& D = L->dir[d];
     e.dhz_in = dhz_buf(d, s & 1);
     e.is_first_step = (s == 0);
@@ -194,12 +209,13 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
   }
 
   using Cfg = UmmaCfg<1, 128, true, false>;   // W_hh read MN-major (columns = hidden units on the TMEM lanes)
-  UmmaBatch<EpiGruBwd> b;
+  using EpiB = EpiGruBwdT<IPN_BF16>;
+  UmmaBatch<EpiB> b;
   memset(&b, 0, sizeof(b));
   b.split_k = 1;
   for (int d = 0; d < L->ndir; ++d) {
     const IpnGruBwdDir& D = L->dir[d];
-    UmmaProblem<EpiGruBwd>& P = b.p[d];
+    UmmaProblem<EpiB>& P = b.p[d];
     P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0;
     HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, 0, 0};
     HostOperand w0{D.w_hh, H, 1, H, 0, 0};
@@ -215,7 +231,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
       b.p[d].seg[1].x_c1 = (int)(t * Bt + L->row0);
       fill_epi(b.p[d].epi, d, s);
     }
-    IPN_PROPAGATE((launch_umma<Cfg, EpiGruBwd>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));
+    IPN_PROPAGATE((launch_umma<Cfg, EpiB>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));
   }
   return IPN_OK;
 }
