@@ -237,6 +237,11 @@ typedef struct {
   void* y;
   long long ld_y;
   int y_col0;
+  int y_reverse_time; /* write y of step s at time slot T-1-s (constraint stack runs on the flipped sequence) */
+  int s_begin, s_end; /* steps processed; s_end == 0 means T */
+  const float* table; /* optional [*, 4H] rows added to the input projection, selected by *tok_scalar (same row for */
+  long long ld_table; /* the whole batch: AnticipationRNN no-teacher-forcing feedback, arnn_model.py:252-256)    */
+  const int* tok_scalar;
 } IpnLstmLayer;
 int ipn_lstm_layer_fwd(const IpnLstmLayer* p, void* stream);
 
@@ -252,6 +257,7 @@ typedef struct {
   int y_col0;
   void* dP; /* [T*B,4H] gradient wrt pre-activations */
   float* ws; /* workspace fp32 [3 * B * H] */
+  int y_reverse_time;
 } IpnLstmLayerBwd;
 int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* p, void* stream);
 
@@ -275,6 +281,10 @@ int ipn_embed_grad(const void* dX, int dx_dt, long long ld_dx, const int* tok, l
 int ipn_argmax_rows(const float* logits, int rows, int V, const IpnRowMap* rowmap, int* tok_out,
                     long long* samples_out, const IpnRowMap* samples_map, void* stream);
 
+/* out[r, col0 + e] = table[idx[r*idx_stride], e] * (row_scale ? row_scale[r] : 1) for e < E; rows with a negative
+ * index give zeros.  Builds concatenated embedding inputs (arnn_model.py:437-532) column block by column block. */
+int ipn_gather_cols(const float* table, int E, const int* idx, long long idx_stride, long long rows, void* out,
+                    int out_dt, long long ld_out, int col0, const float* row_scale, void* stream);
 /* i32 fill */
 int ipn_fill_i32(int* dst, long long n, int value, void* stream);
 /* out[r, c] = sum_s X[s*rows + r, c]  (act dtype in/out): reduces the 6 tick slots of the decoder */

@@ -58,12 +58,14 @@ class GruLayerBwd(C.Structure):
 class LstmLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B", i32), ("H", i32), ("w_hh", vp), ("b_hh", vp),
                 ("P", vp), ("ldP", ll), ("hseq", vp), ("cseq", vp), ("gates", vp), ("y", vp), ("ld_y", ll),
-                ("y_col0", i32)]
+                ("y_col0", i32), ("y_reverse_time", i32), ("s_begin", i32), ("s_end", i32), ("table", vp),
+                ("ld_table", ll), ("tok_scalar", vp)]
 
 
 class LstmLayerBwd(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B", i32), ("H", i32), ("w_hh", vp), ("hseq", vp),
-                ("cseq", vp), ("gates", vp), ("dY", vp), ("ld_dy", ll), ("y_col0", i32), ("dP", vp), ("ws", vp)]
+                ("cseq", vp), ("gates", vp), ("dY", vp), ("ld_dy", ll), ("y_col0", i32), ("dP", vp), ("ws", vp),
+                ("y_reverse_time", i32)]
 
 
 class CeKl(C.Structure):
@@ -108,6 +110,7 @@ SYMBOLS = {
     "ipn_embed_grad": (i32, [vp, i32, ll, vp, ll, i32, i32, vp, i32, vp, vp]),
     "ipn_argmax_rows": (i32, [vp, i32, i32, C.POINTER(RowMap), vp, vp, C.POINTER(RowMap), vp]),
     "ipn_fill_i32": (i32, [vp, ll, i32, vp]),
+    "ipn_gather_cols": (i32, [vp, i32, vp, ll, ll, vp, i32, ll, i32, vp, vp]),
     "ipn_sum_slots": (i32, [vp, i32, ll, i32, ll, i32, vp, ll, vp]),
     "ipn_dlogits_relayout": (i32, [vp, vp, i32, i32, vp, i32, ll, vp]),
     "ipn_dlogits_relayout_mapped": (i32, [vp, vp, i32, i32, C.POINTER(RowMap), vp, i32, ll, vp]),

@@ -52,6 +52,7 @@ __global__ void embed_grad_kernel(const void* dX, int dx_dt, long long ld_dx, co
     const long long r = i / E;
     const int e = (int)(i % E);
     int tk = tok[r];
+    if (tk < 0) continue;       // "no token" rows (zero input) receive no gradient
     if (tk == skip_id) tk = V;  // extra slot
     atomicAdd(&sm[tk * E + e], ld_act(dX, r * ld_dx + e, dx_dt));
   }
@@ -347,6 +348,18 @@ __global__ void convert_2d_kernel(const void* src, int sdt, long long lds, void*
 }
 
 
+__global__ void gather_cols_kernel(const float* table, int E, const int* idx, long long idx_stride, long long rows,
+                                   void* out, int out_dt, long long ld_out, int col0, const float* row_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * E) return;
+  const long long r = i / E;
+  const int e = (int)(i % E);
+  const int k = idx[r * idx_stride];
+  float v = k >= 0 ? table[(long long)k * E + e] : 0.f;
+  if (row_scale != nullptr) v *= row_scale[r];
+  st_act(out, r * ld_out + col0 + e, v, out_dt);
+}
+
 __global__ void fill_i32_kernel(int* dst, long long n, int value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = value;
@@ -545,6 +558,16 @@ int ipn_convert_2d(const void* src, int src_dt, long long ld_src, void* dst, int
   ProfScope prof("convert_2d", 0.0, (double)((double)rows * cols * 6.0), STREAM);
   IPN_REQUIRE(src && dst && rows > 0 && cols > 0, IPN_ERR_ARG, "convert_2d: bad args");
   convert_2d_kernel<<<cdiv(rows * cols, 256), 256, 0, STREAM>>>(src, src_dt, ld_src, dst, dst_dt, ld_dst, rows, cols);
+  IPN_LAUNCH_CHECK();
+  return IPN_OK;
+}
+
+int ipn_gather_cols(const float* table, int E, const int* idx, long long idx_stride, long long rows, void* out,
+                    int out_dt, long long ld_out, int col0, const float* row_scale, void* stream_) {
+  IPN_PROPAGATE(ensure_device());
+  IPN_REQUIRE(table && idx && out && rows > 0 && E > 0 && col0 >= 0 && col0 + E <= ld_out, IPN_ERR_ARG, "gather_cols: bad args");
+  gather_cols_kernel<<<cdiv(rows * E, 256), 256, 0, STREAM>>>(table, E, idx, idx_stride, rows, out, out_dt, ld_out, col0,
+                                                              row_scale);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }

@@ -433,6 +433,10 @@ struct EpiLstmFwd {
     void* y;
     long long ld_y;
     int y_col0;
+    long long ytrow;  // first row of this step in y (differs from trow when the output is time-flipped)
+    const float* table;
+    long long ld_table;
+    const int* tok_scalar;
   };
   struct Col {
     float b[4];
@@ -440,6 +444,11 @@ struct EpiLstmFwd {
   static __device__ __forceinline__ void col_init(const Params& p, int col, Col& cc) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) cc.b[g] = p.b_hh != nullptr ? p.b_hh[g * p.H + col] : 0.f;
+    if (p.table != nullptr) {
+      const long long o = (long long)(*p.tok_scalar) * p.ld_table + col;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) cc.b[g] += p.table[o + (long long)g * p.H];
+    }
   }
   // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
   template <int W> struct Pre {};
@@ -482,7 +491,7 @@ struct EpiLstmFwd {
           st_act(p.gates, o, gi, dt); st_act(p.gates, o + H, gf, dt);
           st_act(p.gates, o + 2 * H, gg, dt); st_act(p.gates, o + 3 * H, go, dt);
         }
-        if (p.y != nullptr) st_act(p.y, TR * p.ld_y + p.y_col0 + col, h, dt);
+        if (p.y != nullptr) st_act(p.y, (p.ytrow + R) * p.ld_y + p.y_col0 + col, h, dt);
       }
     }
   }
@@ -499,6 +508,7 @@ struct LstmBwdPoint {
   const void* dY;
   long long ld_dy;
   int y_col0;
+  long long dytrow;    // first row of this step in dY
   const float* dc_in;  // nullable
   float* dc_out;
   void* dP;  // [T*B, 4H]
@@ -514,7 +524,7 @@ __device__ __forceinline__ void lstm_bwd_pointwise(const LstmBwdPoint& p, int co
     dh[i] = dh_in[i]; gi[i] = gf[i] = gg[i] = go[i] = cp[i] = cc[i] = dci[i] = 0.f;
     if (i < nv) {
       const long long R = row0 + i, TR = p.trow + R;
-      if (p.dY != nullptr) dh[i] += ld_act(p.dY, TR * p.ld_dy + p.y_col0 + col, dt);
+      if (p.dY != nullptr) dh[i] += ld_act(p.dY, (p.dytrow + R) * p.ld_dy + p.y_col0 + col, dt);
       const long long o = TR * 4 * H + col;
       gi[i] = ld_act(p.gates, o, dt); gf[i] = ld_act(p.gates, o + H, dt);
       gg[i] = ld_act(p.gates, o + 2 * H, dt); go[i] = ld_act(p.gates, o + 3 * H, dt);

@@ -37,6 +37,9 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   const int T = L->T, H = L->H, dt = L->act_dt;
   const long long B = L->B;
   const long long es = dt == IPN_BF16 ? 2 : 4;
+  const int s_begin = L->s_begin, s_end = L->s_end > 0 ? L->s_end : T;
+  IPN_REQUIRE(0 <= s_begin && s_begin < s_end && s_end <= T, IPN_ERR_ARG, "lstm_layer_fwd: bad step range");
+  IPN_REQUIRE(!L->table || L->tok_scalar, IPN_ERR_ARG, "lstm_layer_fwd: table without token");
   auto fill_epi = [&](EpiLstmFwd::Params& e, int s) {
     e.H = H; e.act_dt = dt; e.trow = s * B;
     e.P = L->P; e.ldP = L->ldP; e.b_hh = L->b_hh;
@@ -44,12 +47,14 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
     e.c_out = L->cseq + (s + 1) * B * H;
     e.h_out = reinterpret_cast<char*>(L->hseq) + (s + 1) * B * H * es;
     e.gates = L->gates; e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = L->y_col0;
+    e.ytrow = (L->y_reverse_time ? (T - 1 - s) : s) * B;
+    e.table = L->table; e.ld_table = L->ld_table; e.tok_scalar = L->tok_scalar;
   };
   if (L->core == IPN_CORE_SIMT) {
     SimtBatch<EpiLstmFwd> b;
     memset(&b, 0, sizeof(b));
     b.split_k = 1;
-    for (int s = 0; s < T; ++s) {
+    for (int s = s_begin; s < s_end; ++s) {
       SimtProblem<EpiLstmFwd>& P = b.p[0];
       P.nseg = 1; P.M = (int)B; P.N = H; P.gate_stride = H; P.in_dt = dt;
       HostOperand a{L->hseq, H, 0, (T + 1) * B, s * B, 0};
@@ -69,7 +74,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   HostOperand a{L->hseq, H, 0, (T + 1) * B, 0, 0};
   HostOperand w{L->w_hh, H, 0, 4LL * H, 0, 0};
   IPN_PROPAGATE(fill_umma_seg(P.seg[0], a, w, H, Cfg::BR));
-  for (int s = 0; s < T; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
     P.seg[0].x_c1 = (int)(s * B);
     fill_epi(P.epi, s);
     IPN_PROPAGATE((launch_umma<Cfg, EpiLstmFwd>(b, 1, (int)B, H, stream, "lstm_step_fwd_umma")));
@@ -91,6 +96,7 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
     p.c_prev = L->cseq + s * B * H;
     p.c_cur = L->cseq + (s + 1) * B * H;
     p.dY = L->dY; p.ld_dy = L->ld_dy; p.y_col0 = L->y_col0;
+    p.dytrow = (L->y_reverse_time ? (T - 1 - s) : s) * B;
     p.dc_in = (s == T - 1) ? nullptr : L->ws + ((s + 1) & 1) * B * H;
     p.dc_out = L->ws + (s & 1) * B * H;
     p.dP = L->dP;

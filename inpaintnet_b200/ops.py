@@ -119,16 +119,20 @@ def gru_layer_bwd(prec, T, B_total, H, dirs, dhz_ws, dY=0, ld_dy=0, mask=0, ld_m
     L.check(lib().ipn_gru_layer_bwd(C.byref(p), stream()))
 
 
-def lstm_layer_fwd(prec, T, B, H, w_hh, b_hh, P, ldP, hseq, cseq, gates=0, y=0, ld_y=0, y_col0=0):
+def lstm_layer_fwd(prec, T, B, H, w_hh, b_hh, P, ldP, hseq, cseq, gates=0, y=0, ld_y=0, y_col0=0, y_reverse_time=0,
+                   s_begin=0, s_end=0, table=0, ld_table=0, tok_scalar=0):
     p = L.LstmLayer()
+    p.y_reverse_time, p.s_begin, p.s_end = y_reverse_time, s_begin, s_end
+    p.table, p.ld_table, p.tok_scalar = table or None, ld_table, tok_scalar or None
     p.core, p.act_dt, p.T, p.B, p.H = prec.core, prec.act, T, B, H
     p.w_hh, p.b_hh, p.P, p.ldP, p.hseq, p.cseq = w_hh, b_hh or None, P, ldP, hseq, cseq
     p.gates, p.y, p.ld_y, p.y_col0 = gates or None, y or None, ld_y, y_col0
     L.check(lib().ipn_lstm_layer_fwd(C.byref(p), stream()))
 
 
-def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP, ws):
+def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP, ws, y_reverse_time=0):
     p = L.LstmLayerBwd()
+    p.y_reverse_time = y_reverse_time
     p.core, p.act_dt, p.T, p.B, p.H = prec.core, prec.act, T, B, H
     p.w_hh, p.hseq, p.cseq, p.gates, p.dY, p.ld_dy, p.y_col0, p.dP, p.ws = w_hh, hseq, cseq, gates, dY or None, ld_dy, y_col0, dP, ws
     L.check(lib().ipn_lstm_layer_bwd(C.byref(p), stream()))
@@ -163,6 +167,14 @@ def embed_rows(emb, E, tok, rows, out, out_dt, ld_out):
 
 def embed_grad(dX, dx_dt, ld_dx, tok, rows, E, V, demb, skip_id=-1, dskip=0):
     L.check(lib().ipn_embed_grad(dX, dx_dt, ld_dx, tok, rows, E, V, demb, skip_id, dskip or None, stream()))
+
+
+def gather_cols(table, E, idx, idx_stride, rows, out, out_dt, ld_out, col0, row_scale=0):
+    L.check(lib().ipn_gather_cols(table, E, idx, idx_stride, rows, out, out_dt, ld_out, col0, row_scale or None, stream()))
+
+
+def argmax_rows(logits, rows, V, tok_out=0, samples_out=0):
+    L.check(lib().ipn_argmax_rows(logits, rows, V, None, tok_out or None, samples_out or None, None, stream()))
 
 
 def fill_i32(dst, n, value):

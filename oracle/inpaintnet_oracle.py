@@ -329,3 +329,45 @@ def arnn_forward_tf(sd, score, metadata, constraints_loc, num_layers=2, keep_inp
                        sd[f"lstm_generation.{l}.bias_ih_l0"], sd[f"lstm_generation.{l}.bias_hh_l0"])
     hid = torch.relu(linear(x, sd["linear_1.weight"], sd["linear_1.bias"]))    # arnn_model.py:388-392
     return linear(hid, sd["linear_ouput_notes.0.weight"], sd["linear_ouput_notes.0.bias"])  # :396-400
+
+
+def lstm_cell(xp, h, c, w_hh, b_hh):
+    H = h.shape[1]
+    g = xp + h @ w_hh.t() + b_hh
+    i_, f_, g_, o_ = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+    c = f_ * c + i_ * g_
+    return o_ * torch.tanh(c), c
+
+
+def arnn_forward_no_tf(sd, score, metadata, constraints_loc, num_layers=2):
+    """AnticipationRNN without teacher forcing (arnn_model.py:190-259), one voice.  The token fed back to the WHOLE
+    batch at every tick is the argmax of batch element 0 (:252-256); the start symbol is id 0 (:220).
+    Returns logits (B,T,V) and the fed-back tokens (T,)."""
+    B, _, T = score.shape
+    tok = score[:, 0]
+    V1 = sd["note_embeddings.0.weight"].shape[0]
+    masked = torch.where(constraints_loc[:, 0] > 0, tok, torch.full_like(tok, V1 - 1))
+    md = metadata[:, 0]
+    embs_m = [sd[f"metadata_embeddings.{k}.weight"][md[:, :, k]] for k in range(md.shape[-1])]
+    x = torch.flip(torch.cat(embs_m + [sd["note_embeddings.0.weight"][masked]], 2), [1])
+    for l in range(num_layers):
+        x = lstm_layer(x, sd[f"lstm_constraint.{l}.weight_ih_l0"], sd[f"lstm_constraint.{l}.weight_hh_l0"],
+                       sd[f"lstm_constraint.{l}.bias_ih_l0"], sd[f"lstm_constraint.{l}.bias_hh_l0"])
+    cout = torch.flip(x, [1])
+    H = cout.shape[2]
+    hs = [torch.zeros(B, H, dtype=cout.dtype) for _ in range(num_layers)]
+    cs = [torch.zeros(B, H, dtype=cout.dtype) for _ in range(num_layers)]
+    cur = 0
+    outs, fed = [], []
+    for t in range(T):
+        fed.append(cur)
+        inp = torch.cat((sd["note_embeddings.0.weight"][cur].expand(B, -1), cout[:, t]), 1)
+        for l in range(num_layers):
+            xp = inp @ sd[f"lstm_generation.{l}.weight_ih_l0"].t() + sd[f"lstm_generation.{l}.bias_ih_l0"]
+            hs[l], cs[l] = lstm_cell(xp, hs[l], cs[l], sd[f"lstm_generation.{l}.weight_hh_l0"], sd[f"lstm_generation.{l}.bias_hh_l0"])
+            inp = hs[l]
+        w = linear(torch.relu(linear(inp, sd["linear_1.weight"], sd["linear_1.bias"])),
+                   sd["linear_ouput_notes.0.weight"], sd["linear_ouput_notes.0.bias"])
+        outs.append(w)
+        cur = int(torch.argmax(w[0].detach()))
+    return torch.stack(outs, 1), torch.tensor(fed)

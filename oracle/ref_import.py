@@ -45,6 +45,10 @@ class FakeDataset:
     def __repr__(self):
         return f"FakeDataset({len(self.note2index_dicts[0])},{self.n_bars})"
 
+    def empty_score_tensor(self, score_length):
+        import torch
+        return torch.zeros(self.num_voices, score_length).long()
+
 
 _loaded = {}
 

@@ -157,9 +157,11 @@ def arnn_case(name, V, B, seed):
     cl = torch.ones(B, 1, T).long()
     cl[:, :, start:end] = 0
     weights, _ = model._forward_tf(score, metadata, cl)
+    with torch.no_grad():
+        w_notf, gen = model._forward_no_tf(score, metadata, cl)
     fx = dict(V=V, B=B, score=score, metadata=metadata, constraints_loc=cl,
               state_dict={k: v.clone() for k, v in model.state_dict().items()},
-              logits=weights[0].detach().clone())
+              logits=weights[0].detach().clone(), logits_no_tf=w_notf[0].detach().clone(), gen_no_tf=gen.clone())
     torch.save(fx, os.path.join(HERE, name + ".pt"))
     print(name, weights[0].shape)
 

@@ -169,3 +169,31 @@ def test_reference_train_script_runs_unchanged_against_dropin():
         for m in [k for k in sys.modules if k.split(".")[0] in tops]:
             del sys.modules[m]
         sys.modules.update(saved_mods)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tf", [True, False])
+def test_arnn_plumbing_dry_run(prec, tf):
+    if torch.cuda.is_available():
+        pytest.skip("dry run is a CPU-only plumbing check")
+    from inpaintnet_b200.arnn import ConstraintModelGaussianReg, AnticipationRNNGaussianRegTrainer
+    ds = SyntheticFolkDataset(num_notes=20, num_sequences=4)
+    m = ConstraintModelGaussianReg(ds, note_embedding_dim=10, metadata_embedding_dim=2, num_lstm_constraints_units=32,
+                                   num_lstm_generation_units=32, linear_hidden_size=32, num_layers=2, dropout_input_prob=0.2,
+                                   dropout_prob=0.2, unary_constraint=True, teacher_forcing=True).set_precision(prec)
+    keys = set(m.state_dict())
+    assert {"note_embeddings.0.weight", "metadata_embeddings.2.weight", "lstm_constraint.1.weight_hh_l0",
+            "lstm_generation.0.weight_ih_l0", "linear_1.weight", "linear_ouput_notes.0.bias"} <= keys
+    assert m.state_dict()["lstm_generation.0.weight_ih_l0"].shape == (128, 42)
+    m.teacher_forcing_prob = 2.0 if tf else -1.0
+    tr = AnticipationRNNGaussianRegTrainer(ds, m)
+    batch = next(iter(ds.data_loaders(2, split=(0.5, 0.25))[0]))
+    with stubbed():
+        m.train()
+        data = tr.process_batch_data(batch)
+        tr.zero_grad()
+        loss, acc = tr.loss_and_acc_for_batch(data, 0, train=True)
+        loss.backward()
+        tr.step()
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n

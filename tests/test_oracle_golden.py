@@ -92,3 +92,11 @@ def test_arnn_teacher_forced_logits():
     fx = load("arnn_h32")
     logits = O.arnn_forward_tf(fx["state_dict"], fx["score"], fx["metadata"], fx["constraints_loc"])
     assert torch.allclose(logits, fx["logits"], atol=2e-6, rtol=1e-5)
+
+
+def test_arnn_no_teacher_forcing_logits():
+    fx = load("arnn_h32")
+    logits, fed = O.arnn_forward_no_tf(fx["state_dict"], fx["score"], fx["metadata"], fx["constraints_loc"])
+    # gen_chorale[:, 0, t+1] holds the token fed at tick t+1 (the last argmax is never fed)
+    assert torch.equal(fed[1:], fx["gen_no_tf"][0, 0, 1:fed.numel()])
+    assert torch.allclose(logits, fx["logits_no_tf"], atol=5e-6, rtol=1e-5)
