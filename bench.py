@@ -208,6 +208,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr   # model constructors print; stdout carries exactly ONE JSON line
 
     import torch.distributed as dist
     from inpaintnet_b200 import ops
@@ -292,11 +294,12 @@ def main():
     kernels = {}
     if rank == 0:
         ops.prof_enable(True)
-        random.seed(1)
-        for i in range(max(2, args.profile_steps)):
-            model.decoder.teacher_forcing_prob = 2.0 if i % 2 == 0 else -1.0   # one TF step, one argmax step
-            step_resident(i)
-        model.decoder.teacher_forcing_prob = 0.5
+    random.seed(1)
+    for i in range(max(2, args.profile_steps)):   # every rank steps (the gradient all-reduce is collective)
+        model.decoder.teacher_forcing_prob = 2.0 if i % 2 == 0 else -1.0   # one TF step, one argmax step
+        step_resident(i)
+    model.decoder.teacher_forcing_prob = 0.5
+    if rank == 0:
         kernels = ops.prof_report()
         ops.prof_enable(False)
     if world > 1:
@@ -364,7 +367,7 @@ def main():
             "kernels": breakdown,
             "inpaint": inpaint,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,85 @@
+"""Data-parallel parity on real GPUs (needs >= 2; skipped otherwise): two NCCL ranks, each with half of the
+batch, must end a training step with the same parameters as one process that saw the whole batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _step(model, trainer, tokens, eps):
+    from inpaintnet_b200 import engine
+    trainer.zero_grad()
+    with engine.inject_noise(eps=[eps]):
+        loss, acc = trainer.loss_and_acc_for_batch(tokens, 0, train=True)
+    loss.backward()
+    trainer.step()
+    torch.cuda.synchronize()
+    return loss.item()
+
+
+def _build(fx, dev):
+    from inpaintnet_b200.measure_vae import MeasureVAE
+    from inpaintnet_b200.trainer import VAETrainer
+    from inpaintnet_b200.data import SyntheticFolkDataset
+    ds = SyntheticFolkDataset(num_notes=fx["V"])
+    m = MeasureVAE(ds, encoder_hidden_size=fx["H"], decoder_hidden_size=fx["H"], latent_space_dim=fx["Z"])
+    m.load_state_dict(fx["state_dict"])
+    m.to(dev).set_precision("fp32")
+    m.eval()
+    m.decoder.teacher_forcing_prob = 2.0
+    return m, VAETrainer(ds, m, lr=1e-3)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fx = torch.load(os.path.join(G, "mvae_h32.pt"), weights_only=False)
+        B = fx["B"] // world * world
+        per = B // world
+        m, tr = _build(fx, f"cuda:{rank}")
+        sl = slice(rank * per, (rank + 1) * per)
+        _step(m, tr, fx["tokens"][sl].cuda(), fx["eps"][sl])
+        q.put((rank, {k: v.detach().cpu() for k, v in m.state_dict().items()}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_full_batch_step():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    fx = torch.load(os.path.join(G, "mvae_h32.pt"), weights_only=False)
+    B = fx["B"] // world * world
+    m, tr = _build(fx, "cuda:0")
+    _step(m, tr, fx["tokens"][:B].cuda(), fx["eps"][:B])
+    ref = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    for k in ref:
+        assert torch.allclose(res[0][k], res[1][k], atol=0, rtol=0), k            # replicas stay identical
+        assert torch.allclose(res[0][k], ref[k], atol=3e-6, rtol=1e-4), k          # mean-of-means == global mean
