@@ -208,8 +208,12 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
-    real_stdout = sys.stdout
-    sys.stdout = sys.stderr   # model constructors print; stdout carries exactly ONE JSON line
+    # stdout carries exactly ONE JSON line: python-level prints (model constructors) and C-level ones (NCCL's
+    # version banner) are sent to stderr until the final line is written
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_fd, "w")
 
     import torch.distributed as dist
     from inpaintnet_b200 import ops
