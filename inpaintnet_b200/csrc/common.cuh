@@ -191,6 +191,18 @@ __device__ __forceinline__ float tanh_t(float x) {
   else return tanhf(x);
 }
 
+// One input array of an epilogue that the tcgen05 kernel stages through shared memory with bulk copies
+// (rows of 128 output columns): element (row, col) of the problem lives at
+//   ptr + src_row * row_stride_bytes + col * eb,   src_row = gather ? gather[row + gather_add] : row + row_add
+struct StageArr {
+  const char* ptr;
+  long long row_stride_bytes;
+  long long row_add;
+  const int* gather;
+  long long gather_add;
+  int eb;  // bytes per element (1, 2 or 4)
+};
+
 // 3-level affine row map: off = (r / g1) * s1 + ((r % g1) / g2) * s2 + (r % g2) * s3
 __device__ __forceinline__ long long map_row(const IpnRowMap& m, int r) {
   const int a = r / m.g1, rem = r - a * m.g1;

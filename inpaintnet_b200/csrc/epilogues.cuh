@@ -53,7 +53,8 @@ struct EpiLinear {
       cc.base += q * p.split_stride * (p.out_dt == IPN_BF16 ? 2 : 4);
     }
   }
-  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the staged form)
+  static constexpr int NARR = 0;
   template <int W> struct Pre {};
   template <int W>
   static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
@@ -159,11 +160,12 @@ struct GruFwdParams {
     long long ld_final;
     int final_col0;
     int dbg;  // diagnostics (IPN_DBG_EPI): bit0 skip loads, bit1 skip stores
+    int stage;  // 1: the tcgen05 kernel stages the inputs through shared memory (alignment checked on the host)
     unsigned long long* dbg_buf;  // per-CTA phase timestamps (IPN_DBG_TIMING), normally null
   __device__ __forceinline__ float mask_scale_eff() const { return mask != nullptr ? mask_scale : 1.f; }
 };
 
-template <int DT>
+template <int DT, bool STAGE = false>
 struct EpiGruFwdT {
   static constexpr int G = 3;
   using Params = GruFwdParams;
@@ -241,6 +243,74 @@ struct EpiGruFwdT {
       q.mask_bits = bits;
     }
   }
+  // ---- shared-memory staging (tcgen05 kernel): array order P(r,z,n) | table(r,z,n) | h_prev | mask
+  static constexpr int NARR = STAGE ? 8 : 0;
+  static constexpr int NARR_MAX = 8;
+  static __device__ __forceinline__ bool stage_on(const Params& p) { return p.stage != 0 && !(p.dbg & 1); }
+  static __device__ __forceinline__ int stage_arrays(const Params& p, StageArr (&a)[NARR_MAX]) {
+    const int H = p.H;
+    const long long R0 = p.row0, TR0 = p.trow + p.row0;
+    int n = 0;
+    if (p.P != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        a[n++] = StageArr{reinterpret_cast<const char*>(p.P) + (long long)g * H * 2, p.ldP * 2, p.P_bcast ? R0 : TR0, nullptr, 0, 2};
+    }
+    if (p.table != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        a[n++] = StageArr{reinterpret_cast<const char*>(p.table) + (long long)g * H * 4, p.ld_table * 4, 0, p.tok, TR0, 4};
+    }
+    a[n++] = StageArr{reinterpret_cast<const char*>(p.h_prev), (long long)H * 2, R0, nullptr, 0, 2};
+    if (p.y != nullptr && p.mask != nullptr)
+      a[n++] = StageArr{reinterpret_cast<const char*>(p.mask) + p.y_col0, p.ld_mask, TR0, nullptr, 0, 1};
+    return n;
+  }
+  // fills Pre from a staged chunk: `chunk` = base of the chunk buffer, arrays laid out in stage_arrays order as
+  // [16 rows][128 cols]; lc = column inside the tile, rr0 = first row inside the chunk
+  template <int W>
+  static __device__ __forceinline__ void preload_smem(const Params& p, const Col& cc, const char* chunk, int lc, int rr0,
+                                                      Pre<W>& q) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) { q.pr[i] = cc.cr; q.pz[i] = cc.cz; q.pn[i] = cc.cn; }
+    q.mask_bits = 0xffffffffu;
+    const char* s = chunk;
+    if (p.P != nullptr) {
+      const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(s);
+      const __nv_bfloat16* a1 = a0 + 16 * 128;
+      const __nv_bfloat16* a2 = a1 + 16 * 128;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const int o = (rr0 + i) * 128 + lc;
+        q.pr[i] += __bfloat162float(a0[o]); q.pz[i] += __bfloat162float(a1[o]); q.pn[i] += __bfloat162float(a2[o]);
+      }
+      s += 3 * 16 * 128 * 2;
+    }
+    if (p.table != nullptr) {
+      const float* a0 = reinterpret_cast<const float*>(s);
+      const float* a1 = a0 + 16 * 128;
+      const float* a2 = a1 + 16 * 128;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const int o = (rr0 + i) * 128 + lc;
+        q.pr[i] += a0[o]; q.pz[i] += a1[o]; q.pn[i] += a2[o];
+      }
+      s += 3 * 16 * 128 * 4;
+    }
+    {
+      const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(s);
+#pragma unroll
+      for (int i = 0; i < W; ++i) q.hp[i] = __bfloat162float(a0[(rr0 + i) * 128 + lc]);
+      s += 16 * 128 * 2;
+    }
+    if (p.y != nullptr && p.mask != nullptr) {
+      const unsigned char* a0 = reinterpret_cast<const unsigned char*>(s);
+      unsigned bits = 0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) bits |= (a0[(rr0 + i) * 128 + lc] ? 1u : 0u) << i;
+      q.mask_bits = bits;
+    }
+  }
   // gate math + stores
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
@@ -266,12 +336,68 @@ struct EpiGruFwdT {
       }
     }
   }
+  // direct form (no staging): loads issued array by array straight into the math registers
   template <int W>
   static __device__ __forceinline__ void applyT(const Params& p, const Col& cc, int col, int row0, int nv,
                                                 float (&acc)[3][W]) {
-    Pre<W> q;
-    preload<W>(p, cc, col, row0, nv, q);
-    applyT<W>(p, cc, col, row0, nv, acc, q);
+    const int H = p.H, dt = p.act_dt;
+    long long R[W], TR[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      R[i] = p.row0 + row0 + min(i, nv - 1);
+      TR[i] = p.trow + R[i];
+    }
+    float pr[W], pz[W], pn[W], hp[W], mk[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) { pr[i] = 0.f; pz[i] = 0.f; pn[i] = 0.f; mk[i] = 1.f; }
+    const bool ld_on = !(p.dbg & 1);
+    if (p.P != nullptr && ld_on) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const long long o = (p.P_bcast ? R[i] : TR[i]) * p.ldP + col;
+        pr[i] = ld_t<DT>(p.P, o, dt); pz[i] = ld_t<DT>(p.P, o + H, dt); pn[i] = ld_t<DT>(p.P, o + 2 * H, dt);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) hp[i] = ld_on ? ld_t<DT>(p.h_prev, R[i] * H + col, dt) : 0.f;
+    if (p.y != nullptr && p.mask != nullptr && ld_on) {
+      unsigned char mb[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) mb[i] = p.mask[TR[i] * p.ld_mask + p.y_col0 + col];
+#pragma unroll
+      for (int i = 0; i < W; ++i) mk[i] = mb[i] ? p.mask_scale : 0.f;
+    }
+    if (p.table != nullptr && ld_on) {
+      int tk[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) tk[i] = p.tok[TR[i]];
+      float tr[W], tz[W], tn[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const long long o = (long long)tk[i] * p.ld_table + col;
+        tr[i] = p.table[o]; tz[i] = p.table[o + H]; tn[i] = p.table[o + 2 * H];
+      }
+#pragma unroll
+      for (int i = 0; i < W; ++i) { pr[i] += tr[i]; pz[i] += tz[i]; pn[i] += tn[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float r = sigmoid_t<DT>(pr[i] + cc.cr + acc[0][i] + cc.br);
+      const float z = sigmoid_t<DT>(pz[i] + cc.cz + acc[1][i] + cc.bz);
+      const float hn = acc[2][i] + cc.bn;
+      const float n = tanh_t<DT>(pn[i] + cc.cn + r * hn);
+      const float h = (1.f - z) * n + z * hp[i];
+      if (i < nv && !(p.dbg & 2)) {
+        st_t<DT>(p.h_out, R[i] * H + col, h, dt);
+        if (p.gates != nullptr) {
+          const long long go = TR[i] * 4 * H + col;
+          st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
+          st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
+        }
+        if (p.y != nullptr) st_t<DT>(p.y, TR[i] * p.ld_y + p.y_col0 + col, h * mk[i], dt);
+        if (p.final_out != nullptr) st_act(p.final_out, R[i] * p.ld_final + p.final_col0 + col, h, p.final_dt);
+      }
+    }
   }
 };
 using EpiGruFwd = EpiGruFwdT<-1>;
@@ -373,7 +499,8 @@ struct EpiGruBwdT {
   using Params = GruBwdParams;
   struct Col {};
   static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
-  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the staged form)
+  static constexpr int NARR = 0;
   template <int W> struct Pre {};
   template <int W>
   static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
@@ -450,7 +577,8 @@ struct EpiLstmFwd {
       for (int g = 0; g < 4; ++g) cc.b[g] += p.table[o + (long long)g * p.H];
     }
   }
-  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the staged form)
+  static constexpr int NARR = 0;
   template <int W> struct Pre {};
   template <int W>
   static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}
@@ -559,7 +687,8 @@ struct EpiLstmBwd {
   };
   struct Col {};
   static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
-  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the pipelined form)
+  // epilogues without a separate load phase: empty preload (see EpiGruFwdT for the staged form)
+  static constexpr int NARR = 0;
   template <int W> struct Pre {};
   template <int W>
   static __device__ __forceinline__ void preload(const Params&, const Col&, int, int, int, Pre<W>&) {}

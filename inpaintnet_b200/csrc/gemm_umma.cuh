@@ -22,7 +22,7 @@ namespace ipn {
 
 constexpr int UMMA_BC = 128;       // output columns per tile (TMEM lanes, MMA M)
 constexpr int UMMA_BK = 64;        // bf16 elements per stage along K (= 128 bytes, one swizzle row)
-constexpr int UMMA_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 warps per TMEM lane quadrant)
+constexpr int UMMA_THREADS = 320;  // default: warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 warps per TMEM lane quadrant)
 
 struct UmmaSeg {
   alignas(64) CUtensorMap tmW;
@@ -48,8 +48,11 @@ struct UmmaBatch {
 };
 
 // G gates, BR output rows per tile, TW / TX: W / X operand is MN-major (row-major [K, cols|rows])
-template <int G_, int BR_, bool TW_, bool TX_, int MAX_SMEM_KB = 110>
+template <int G_, int BR_, bool TW_, bool TX_, int MAX_SMEM_KB = 110, int EPI_WARPS_ = 8>
 struct UmmaCfg {
+  static constexpr int EPI_WARPS = EPI_WARPS_;            // multiple of 4 (warps per TMEM lane quadrant x 4)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS_;
+  static constexpr int PARTS = EPI_WARPS_ / 4;            // warps sharing a lane quadrant take every PARTS-th chunk
   static constexpr int G = G_;
   static constexpr int BR = BR_;
   static constexpr bool TW = TW_;
@@ -59,7 +62,7 @@ struct UmmaCfg {
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM_KB * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int ACC_COLS = G_ * BR_;
   static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
@@ -86,7 +89,7 @@ __device__ __forceinline__ void dbg_stamp(const typename Epi::Params& p, int slo
 }
 
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(UMMA_THREADS, Cfg::CTAS_PER_SM)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM)
 umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   static_assert(Epi::G == Cfg::G, "epilogue / tile gate count mismatch");
   constexpr int G = Cfg::G, BR = Cfg::BR, STAGES = Cfg::STAGES;
@@ -95,7 +98,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* st_full = tmem_full_bar + 1;   // epilogue-input staging ring (8 chunk buffers max)
+  uint64_t* st_empty = st_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_empty + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +126,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
         ptx::mbar_init(&empty_bar[s], 1);
       }
       ptx::mbar_init(tmem_full_bar, 1);
+      for (int s = 0; s < 8; ++s) {
+        ptx::mbar_init(&st_full[s], 1);
+        ptx::mbar_init(&st_empty[s], 4);  // the 4 lane-quadrant warps that consume a chunk
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -139,6 +148,25 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) dbg_stamp<Epi>(P.epi, 1);
+
+  // Epilogue-input staging: once the accumulators are complete the mainloop stages are dead, so warp 0
+  // refills them with the epilogue's input rows (bulk copies of up to 128 columns per row) chunk by chunk
+  // (16 rows), and the epilogue warps read their operands from shared memory instead of stalling on
+  // global loads.  A ring of nbuf chunk buffers with full/empty mbarriers handles chunks that do not all fit.
+  bool stage_on = false;
+  int st_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int st_na = 0, st_chunk_bytes = 0, st_nbuf = 1;
+  StageArr st_arr[Epi::NARR > 0 ? 8 : 1];
+  if constexpr (Epi::NARR > 0) {
+    if (Epi::stage_on(P.epi) && nchunks > 0) {
+      st_na = Epi::stage_arrays(P.epi, st_arr);
+#pragma unroll
+      for (int a = 0; a < Epi::NARR; ++a) st_off[a + 1] = st_off[a] + (a < st_na ? 16 * 128 * st_arr[a].eb : 0);
+      st_chunk_bytes = (st_off[Epi::NARR] + 127) & ~127;
+      st_nbuf = min(8, (STAGES * Cfg::STAGE_BYTES) / st_chunk_bytes);
+      stage_on = st_nbuf >= 1;
+    }
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -175,6 +203,40 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
       }
       dbg_stamp<Epi>(P.epi, 2);  // all TMA loads issued
     }
+    if constexpr (Epi::NARR > 0) {
+      if (stage_on) {
+        __syncwarp();
+        ptx::mbar_wait(tmem_full_bar, 0);  // every MMA has finished reading the stage buffers
+        const int ncols = min(UMMA_BC, P.N - c0);
+        int row_bytes = 0;
+#pragma unroll
+        for (int a = 0; a < Epi::NARR; ++a)
+          if (a < st_na) row_bytes += ncols * st_arr[a].eb;
+        for (int c = 0; c < BR / 16; ++c) {
+          const int row0 = r0 + c * 16;
+          if (row0 >= P.M) break;
+          const int nvr = min(16, P.M - row0);
+          const int b = c % st_nbuf;
+          if (c >= st_nbuf) ptx::mbar_wait(&st_empty[b], ((c / st_nbuf) - 1) & 1);
+          if (lane == 0) ptx::mbar_arrive_expect_tx(&st_full[b], (uint32_t)(nvr * row_bytes));
+          __syncwarp();
+          uint8_t* dst = smem + b * st_chunk_bytes;
+          if (lane < nvr) {
+#pragma unroll
+            for (int a = 0; a < Epi::NARR; ++a) {
+              if (a < st_na) {
+                const StageArr& A = st_arr[a];
+                const long long row = row0 + lane;
+                const long long src_row = A.gather != nullptr ? (long long)A.gather[row + A.gather_add] : row + A.row_add;
+                ptx::bulk_copy_g2s(dst + st_off[a] + lane * 128 * A.eb,
+                                   A.ptr + src_row * A.row_stride_bytes + (long long)c0 * A.eb, (uint32_t)(ncols * A.eb),
+                                   &st_full[b]);
+              }
+            }
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && nchunks > 0) {
@@ -206,7 +268,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 16-row chunks
+    const int half = (warp - 2) >> 2;  // the PARTS warps of a quadrant take every PARTS-th 16-row chunk
     const int col = c0 + q * 32 + lane;
     const bool col_ok = col < P.N;
     typename Epi::Col cc;
@@ -217,7 +279,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
     }
     if (threadIdx.x == 64) dbg_stamp<Epi>(P.epi, 4);  // accumulators complete
 #pragma unroll 1
-    for (int c = half; c < BR / 16; c += 2) {
+    for (int c = half; c < BR / 16; c += Cfg::PARTS) {
       const int row0 = r0 + c * 16;
       if (row0 >= P.M) break;  // warp uniform
       float acc[G][16];
@@ -232,10 +294,36 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
       }
+      const int nv = min(16, P.M - row0);
+      if constexpr (Epi::NARR > 0) {
+        if (stage_on) {
+          const int b = c % st_nbuf;
+          ptx::mbar_wait(&st_full[b], (c / st_nbuf) & 1);
+          const char* chunk = reinterpret_cast<const char*>(smem) + b * st_chunk_bytes;
+          typename Epi::template Pre<8> pre[2];
+          if (col_ok) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) Epi::template preload_smem<8>(P.epi, cc, chunk, q * 32 + lane, h * 8, pre[h]);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&st_empty[b]);  // this warp is done with the chunk buffer
+          if (col_ok) {
+            float a8[G][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a8[g][i] = acc[g][h * 8 + i];
+              const int nvh = nv - h * 8;
+              if (nvh > 0) Epi::template applyT<8>(P.epi, cc, col, row0 + h * 8, min(8, nvh), a8, pre[h]);
+            }
+          }
+          continue;
+        }
+      }
       if (col_ok) {
-        const int nv = min(16, P.M - row0);
-        // two phases of 8 rows (bounds the registers held by an epilogue's load phase).  Issuing the next
-        // phase's loads early (register double buffering) was measured slower: it spills.
+        // two phases of 8 rows (bounds the registers held by an epilogue's load phase)
         float a8[G][8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {

@@ -59,6 +59,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
 
   static const int dbg_epi = getenv("IPN_DBG_EPI") ? atoi(getenv("IPN_DBG_EPI")) : 0;
   static const int gru_br = getenv("IPN_GRU_BR") ? atoi(getenv("IPN_GRU_BR")) : 128;
+  static const int stage_enable = getenv("IPN_STAGE") ? 2 : 0;   // IPN_STAGE=1 opts in to smem staging
   auto fill_epi = [&](GruFwdParams& e, const IpnGruDir& D, int s) {
     const int t = D.reverse ? T - 1 - s : s;
     const int in_slot = D.reverse ? t + 1 : t, out_slot = D.reverse ? t : t + 1;
@@ -81,6 +82,14 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     e.final_col0 = D.final_col0;
     e.dbg = dbg_epi;
     e.dbg_buf = g_dbg_timing;
+    // shared-memory staging of the epilogue inputs needs 16-byte aligned row segments for every tile
+    auto al16 = [](const void* ptr, long long stride_bytes) {
+      return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && stride_bytes % 16 == 0);
+    };
+    e.stage = (stage_enable == 2 && L->core == IPN_CORE_UMMA && H % 16 == 0 && al16(D.P, D.ldP * 2) &&
+               al16(D.table, D.ld_table * 4) && al16(D.hseq, H * 2) && (Bt * H * 2) % 16 == 0 &&
+               al16(L->mask, L->ld_mask) && D.y_col0 % 16 == 0)
+                  ? 1 : 0;
     return in_slot;
   };
 
@@ -103,9 +112,11 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     return IPN_OK;
   }
 
-  auto run = [&](auto cfg_tag) -> int {
+  auto run_t = [&](auto cfg_tag, auto epi_tag) -> int {
     using Cfg = decltype(cfg_tag);
-    using Epi = EpiGruFwdT<IPN_BF16>;
+    // shared-memory staging of the epilogue inputs (EpiGruFwdT<.., true>) is implemented but measured slower
+    // than direct loads in round 1 (256-byte bulk copies are TMA-issue bound; registers spill): opt-in only.
+    using Epi = decltype(epi_tag);
     UmmaBatch<Epi> b;
     memset(&b, 0, sizeof(b));
     b.split_k = 1;
@@ -127,8 +138,13 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     return IPN_OK;
   };
   // 128 hidden units x BR rows x 3 gates per CTA
+  auto run = [&](auto cfg_tag) -> int {
+    if (stage_enable == 2) return run_t(cfg_tag, EpiGruFwdT<IPN_BF16, true>{});
+    return run_t(cfg_tag, EpiGruFwdT<IPN_BF16, false>{});
+  };
   if (gru_br == 64) return run(UmmaCfg<3, 64, false, false, 112>{});    // 192 TMEM columns, 2 CTAs/SM
   if (gru_br == 32) return run(UmmaCfg<3, 32, false, false, 112>{});    // 96 TMEM columns, 2 CTAs/SM
+  if (gru_br == 1128) return run(UmmaCfg<3, 128, false, false, 200, 16>{});  // 16 epilogue warps
   return run(UmmaCfg<3, 128, false, false, 200>{});                     // 384 TMEM columns, 1 CTA/SM
 }
 

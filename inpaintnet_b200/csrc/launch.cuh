@@ -85,7 +85,7 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
   }
   dim3 grid(cdiv(maxN, UMMA_BC), cdiv(maxM, Cfg::BR), nprob * batch.split_k);
   IPN_REQUIRE(grid.y <= 65535, IPN_ERR_ARG, "too many row tiles (%u) for one launch", grid.y);
-  kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(batch);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(batch);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }
