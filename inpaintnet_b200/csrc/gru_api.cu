@@ -224,30 +224,37 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     return IPN_OK;
   }
 
-  using Cfg = UmmaCfg<1, 128, true, false>;   // W_hh read MN-major (columns = hidden units on the TMEM lanes)
-  using EpiB = EpiGruBwdT<IPN_BF16>;
-  UmmaBatch<EpiB> b;
-  memset(&b, 0, sizeof(b));
-  b.split_k = 1;
-  for (int d = 0; d < L->ndir; ++d) {
-    const IpnGruBwdDir& D = L->dir[d];
-    UmmaProblem<EpiB>& P = b.p[d];
-    P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0;
-    HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, 0, 0};
-    HostOperand w0{D.w_hh, H, 1, H, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[0], a0, w0, 2 * H, Cfg::BR));
-    HostOperand a1{D.dGn, H, 0, (long long)T * Bt, 0, 0};
-    HostOperand w1{D.w_hh, H, 1, H, 0, 2LL * H};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[1], a1, w1, H, Cfg::BR));
-  }
-  for (int s = T - 1; s >= 0; --s) {
+  static const int bwd_cfg = getenv("IPN_GRU_BWD_CFG") ? atoi(getenv("IPN_GRU_BWD_CFG")) : 0;
+  auto run = [&](auto cfg_tag) -> int {
+    using Cfg = decltype(cfg_tag);   // W_hh read MN-major (columns = hidden units on the TMEM lanes)
+    using EpiB = EpiGruBwdT<IPN_BF16>;
+    UmmaBatch<EpiB> b;
+    memset(&b, 0, sizeof(b));
+    b.split_k = 1;
     for (int d = 0; d < L->ndir; ++d) {
-      const int t = L->dir[d].reverse ? T - 1 - s : s;
-      b.p[d].seg[0].x_c1 = (int)(t * Bt + L->row0);
-      b.p[d].seg[1].x_c1 = (int)(t * Bt + L->row0);
-      fill_epi(b.p[d].epi, d, s);
+      const IpnGruBwdDir& D = L->dir[d];
+      UmmaProblem<EpiB>& P = b.p[d];
+      P.nseg = 2; P.M = L->nrows; P.N = H; P.gate_stride = 0;
+      HostOperand a0{D.dP, 3LL * H, 0, (long long)T * Bt, 0, 0};
+      HostOperand w0{D.w_hh, H, 1, H, 0, 0};
+      IPN_PROPAGATE(fill_umma_seg(P.seg[0], a0, w0, 2 * H, Cfg::BR));
+      HostOperand a1{D.dGn, H, 0, (long long)T * Bt, 0, 0};
+      HostOperand w1{D.w_hh, H, 1, H, 0, 2LL * H};
+      IPN_PROPAGATE(fill_umma_seg(P.seg[1], a1, w1, H, Cfg::BR));
     }
-    IPN_PROPAGATE((launch_umma<Cfg, EpiB>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));
-  }
-  return IPN_OK;
+    for (int s = T - 1; s >= 0; --s) {
+      for (int d = 0; d < L->ndir; ++d) {
+        const int t = L->dir[d].reverse ? T - 1 - s : s;
+        b.p[d].seg[0].x_c1 = (int)(t * Bt + L->row0);
+        b.p[d].seg[1].x_c1 = (int)(t * Bt + L->row0);
+        fill_epi(b.p[d].epi, d, s);
+      }
+      IPN_PROPAGATE((launch_umma<Cfg, EpiB>(b, L->ndir, L->nrows, H, stream, "gru_step_bwd_umma")));
+    }
+    return IPN_OK;
+  };
+  if (bwd_cfg == 0) return run(UmmaCfg<1, 128, true, false>{});            // 2 CTAs/SM (96-register cap)
+  if (bwd_cfg == 2) return run(UmmaCfg<1, 256, true, false, 200>{});       // 256-row tiles, 1 CTA/SM
+  if (bwd_cfg == 3) return run(UmmaCfg<1, 128, true, false, 200, 16>{});   // 16 epilogue warps
+  return run(UmmaCfg<1, 128, true, false, 200>{});                         // 128-row tiles, 1 CTA/SM, no spills
 }
