@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IPN_ABI_VERSION 1
+#define IPN_ABI_VERSION 2
 
 /* status codes */
 #define IPN_OK 0
@@ -134,7 +134,12 @@ int ipn_gemm(const IpnGemm* g, void* stream);
  * (c) a constant vector `pvec`; b_ih must already be folded into one of them.
  * Rows: a "slot" holds B_total rows; the call processes rows [row0, row0+nrows) of each slot.
  * hseq: [(T+1)*B_total, H]. forward dir: slot 0 = h0, slot t+1 = h_t. reverse dir: slot T = h0,
- * slot t = h_t.  gates: [T*B_total, 4H] = (r, z, n, W_hn h + b_hn) saved for backward (nullable).
+ * slot t = h_t.  gates: opaque buffer of T*B_total*ipn_gru_gates_cols(H) elements saved for backward
+ * (nullable): (r, z, n, W_hn h + b_hn [, h_prev]); its internal layout is private to the fwd/bwd pair.
+ * ws: optional workspace of ipn_gru_layer_fwd_ws_bytes() bytes.  When it is supplied and the shape is
+ * eligible (tcgen05 core, H % 64 == 0, H <= 512, B_total % 128 == 0, full row and step range) the whole
+ * layer runs as ONE persistent kernel (all timesteps, W_hh streamed from L2, h_t handed from step to step
+ * inside the CTA); otherwise one fused kernel is launched per timestep.
  * y: layer output rows t*B_total+b, this direction at columns [y_col0, y_col0+H), multiplied by
  * keep-mask*mask_scale when mask != null (inter-layer dropout, train mode).
  * final_out: h after the last processed step, at columns [final_col0, +H) of row b (nullable).
@@ -175,8 +180,14 @@ typedef struct {
   void* final_out;
   int final_dt;
   long long ld_final;
+  void* ws; /* nullable */
+  long long ws_bytes;
 } IpnGruLayer;
 int ipn_gru_layer_fwd(const IpnGruLayer* p, void* stream);
+/* bytes of workspace with which ipn_gru_layer_fwd runs the persistent kernel; 0 = not eligible */
+long long ipn_gru_layer_fwd_ws_bytes(const IpnGruLayer* p);
+/* elements per (timestep, batch row) of the `gates` buffer */
+int ipn_gru_gates_cols(int H);
 
 /* GRU layer backward (BPTT, reverse-time).  replaces the autograd of torch.nn.GRU reached from
  * utils/trainer.py:150 (loss.backward()).  Produces, time-ordered: dP [T*B_total,3H] (gradient wrt
@@ -215,8 +226,15 @@ typedef struct {
   long long ld_mask;
   float mask_scale;
   float* dhz_ws; /* workspace fp32 [ndir * 2 * B_total * H] */
+  void* ws;      /* nullable; see ipn_gru_layer_bwd_ws_bytes */
+  long long ws_bytes;
+  int gates_persist; /* 1 when `gates` was written by the persistent forward kernel (ipn_gru_layer_fwd called with a
+                        workspace on an eligible shape), 0 when it was written by the per-step kernels */
 } IpnGruLayerBwd;
 int ipn_gru_layer_bwd(const IpnGruLayerBwd* p, void* stream);
+/* workspace for the persistent backward kernel; 0 = not eligible (the per-step kernels then read either
+ * gates layout, selected by gates_persist). */
+long long ipn_gru_layer_bwd_ws_bytes(const IpnGruLayerBwd* p);
 
 /* ------------------------------------------------------------------------------------------
  * LSTM layer forward/backward (uni-directional, zero initial state), gate rows [i; f; g; o].

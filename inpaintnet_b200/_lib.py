@@ -41,7 +41,7 @@ class GruLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B_total", i32), ("H", i32), ("row0", i32),
                 ("nrows", i32), ("s_begin", i32), ("s_end", i32), ("ndir", i32), ("dir", GruDir * 2), ("y", vp),
                 ("ld_y", ll), ("mask", vp), ("ld_mask", ll), ("mask_scale", f32), ("final_out", vp),
-                ("final_dt", i32), ("ld_final", ll)]
+                ("final_dt", i32), ("ld_final", ll), ("ws", vp), ("ws_bytes", ll)]
 
 
 class GruBwdDir(C.Structure):
@@ -52,7 +52,7 @@ class GruBwdDir(C.Structure):
 class GruLayerBwd(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B_total", i32), ("H", i32), ("row0", i32),
                 ("nrows", i32), ("ndir", i32), ("dir", GruBwdDir * 2), ("dY", vp), ("ld_dy", ll), ("mask", vp),
-                ("ld_mask", ll), ("mask_scale", f32), ("dhz_ws", vp)]
+                ("ld_mask", ll), ("mask_scale", f32), ("dhz_ws", vp), ("ws", vp), ("ws_bytes", ll), ("gates_persist", i32)]
 
 
 class LstmLayer(C.Structure):
@@ -102,6 +102,9 @@ SYMBOLS = {
     "ipn_gemm": (i32, [C.POINTER(Gemm), vp]),
     "ipn_gru_layer_fwd": (i32, [C.POINTER(GruLayer), vp]),
     "ipn_gru_layer_bwd": (i32, [C.POINTER(GruLayerBwd), vp]),
+    "ipn_gru_layer_fwd_ws_bytes": (ll, [C.POINTER(GruLayer)]),
+    "ipn_gru_layer_bwd_ws_bytes": (ll, [C.POINTER(GruLayerBwd)]),
+    "ipn_gru_gates_cols": (i32, [i32]),
     "ipn_lstm_layer_fwd": (i32, [C.POINTER(LstmLayer), vp]),
     "ipn_lstm_layer_bwd": (i32, [C.POINTER(LstmLayerBwd), vp]),
     "ipn_tokens_time_major": (i32, [vp, i32, i32, i32, vp, vp, vp]),

@@ -409,7 +409,8 @@ using EpiGruFwd = EpiGruFwdT<-1>;
 struct GruBwdPoint {
   int H, act_dt, row0;
   long long trow;       // t * B_total of the step whose gates are differentiated
-  const void* gates;    // [T*B_total, 4H]
+  const void* gates;    // [T*B_total, 4H], or the blocked 5-array layout of the persistent forward kernel
+  int gates_blocked;
   const void* h_prev;   // slot base of the state that ENTERED this step
   const void* dY;       // time-ordered, nullable
   long long ld_dy;
@@ -436,11 +437,15 @@ __device__ __forceinline__ void gru_bwd_pointwise(const GruBwdPoint& p, int col,
   }
   // ---- phase 1: all loads, array by array (see EpiGruFwdT)
   float r[W], z[W], n[W], hn[W], hp[W], dy[W], dn_[W];
+  // gate array stride; blocked layout (gru_persist.cuh): vec16(R, a, u) = ((R/128*5 + a)*(H/8) + u/8)*128 + R%128
+  const long long gs = p.gates_blocked ? (long long)H * 128 : (long long)H;
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    const long long go = TR[i] * 4 * H + col;
-    r[i] = ld_t<DT>(p.gates, go, dt); z[i] = ld_t<DT>(p.gates, go + H, dt);
-    n[i] = ld_t<DT>(p.gates, go + 2 * H, dt); hn[i] = ld_t<DT>(p.gates, go + 3 * H, dt);
+    const long long go = p.gates_blocked
+                             ? ((((TR[i] >> 7) * 5) * (H >> 3) + (col >> 3)) * 128 + (TR[i] & 127)) * 8 + (col & 7)
+                             : TR[i] * 4 * H + col;
+    r[i] = ld_t<DT>(p.gates, go, dt); z[i] = ld_t<DT>(p.gates, go + gs, dt);
+    n[i] = ld_t<DT>(p.gates, go + 2 * gs, dt); hn[i] = ld_t<DT>(p.gates, go + 3 * gs, dt);
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) hp[i] = ld_t<DT>(p.h_prev, R[i] * H + col, dt);

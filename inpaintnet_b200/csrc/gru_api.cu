@@ -35,11 +35,29 @@ static int check_layer_common(int core, int act_dt, int T, int B_total, int H, i
   return IPN_OK;
 }
 
+// gru_persist.cu / gru_persist_bwd.cu
+bool gru_persist_fwd_shape_ok(const IpnGruLayer* L);
+long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L);
+int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStream_t stream);
+bool gru_persist_bwd_shape_ok(const IpnGruLayerBwd* L);
+long long gru_persist_bwd_ws_bytes(const IpnGruLayerBwd* L);
+int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaStream_t stream);
+
 }  // namespace ipn
 
 using namespace ipn;
 
-static unsigned long long* g_dbg_timing = nullptr;
+extern "C" long long ipn_gru_layer_fwd_ws_bytes(const IpnGruLayer* L) {
+  if (L == nullptr || L->T <= 0 || L->B_total <= 0 || L->H <= 0 || (L->ndir != 1 && L->ndir != 2)) return 0;
+  return gru_persist_fwd_ws_bytes(L);
+}
+extern "C" long long ipn_gru_layer_bwd_ws_bytes(const IpnGruLayerBwd* L) {
+  if (L == nullptr || L->T <= 0 || L->B_total <= 0 || L->H <= 0 || (L->ndir != 1 && L->ndir != 2)) return 0;
+  return gru_persist_bwd_ws_bytes(L);
+}
+extern "C" int ipn_gru_gates_cols(int H) { return 5 * H; }
+
+namespace ipn { unsigned long long* g_dbg_timing = nullptr; }
 extern "C" void ipn_dbg_set_timing_buffer(void* dev_ptr) { g_dbg_timing = reinterpret_cast<unsigned long long*>(dev_ptr); }
 
 extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
@@ -56,6 +74,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     IPN_REQUIRE(D.P || D.table || D.pvec, IPN_ERR_ARG, "gru_layer_fwd: no input projection source (dir %d)", d);
     IPN_REQUIRE(!D.table || D.tok, IPN_ERR_ARG, "gru_layer_fwd: table without tokens");
   }
+  if (L->ws != nullptr && gru_persist_fwd_shape_ok(L)) return gru_persist_fwd(L, L->ws, L->ws_bytes, stream);
 
   static const int dbg_epi = getenv("IPN_DBG_EPI") ? atoi(getenv("IPN_DBG_EPI")) : 0;
   static const int gru_br = getenv("IPN_GRU_BR") ? atoi(getenv("IPN_GRU_BR")) : 128;
@@ -160,6 +179,9 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     const IpnGruBwdDir& D = L->dir[d];
     IPN_REQUIRE(D.w_hh && D.hseq && D.gates && D.dP && D.dGn, IPN_ERR_ARG, "gru_layer_bwd: null pointer (dir %d)", d);
   }
+  IPN_REQUIRE(!L->gates_persist || (L->B_total % 128 == 0 && H % 8 == 0 && dt == IPN_BF16), IPN_ERR_ARG,
+              "gru_layer_bwd: gates_persist set for a shape the persistent forward kernel cannot have produced");
+  if (L->gates_persist && L->ws != nullptr && gru_persist_bwd_shape_ok(L)) return gru_persist_bwd(L, L->ws, L->ws_bytes, stream);
   auto dhz_buf = [&](int d, int which) { return L->dhz_ws + ((long long)d * 2 + which) * Bt * H; };
 
   // describes the pointwise differentiation of processing step s for direction d
@@ -169,6 +191,7 @@ extern "C" int ipn_gru_layer_bwd(const IpnGruLayerBwd* L, void* stream_) {
     const int in_slot = D.reverse ? t + 1 : t;
     p.H = H; p.act_dt = dt; p.row0 = L->row0; p.trow = (long long)t * Bt;
     p.gates = D.gates;
+    p.gates_blocked = L->gates_persist;
     p.h_prev = slot_ptr(D.hseq, in_slot, Bt, H, dt);
     p.dY = L->dY; p.ld_dy = L->ld_dy; p.y_col0 = D.y_col0; p.mask = L->mask; p.ld_mask = L->ld_mask;
     p.mask_scale = L->mask_scale;

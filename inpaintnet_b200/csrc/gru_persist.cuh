@@ -1,0 +1,63 @@
+// Persistent GRU layer kernels (forward and backward): one launch runs ALL timesteps of a layer.
+//
+// A CTA owns a tile of 128 batch rows of one direction for the whole sequence, so the serial chain
+// needs no grid-wide synchronisation: the only cross-step hand-off is inside the CTA (TMA store of
+// h_t -> TMA reload as the next step's A operand, tracked per 64-unit k-block with mbarriers).
+// "Lanes = batch rows": MMA M = 128 rows (TMEM lanes), N = 3 gates x 64 hidden units per chunk
+// (forward) so one thread holds r, z, n of 16 consecutive units of ITS row per tcgen05.ld.  All
+// per-element traffic of the epilogue uses the BLOCKED layout below (16-byte vectors, fully
+// coalesced 512-byte warp accesses, no shared-memory staging); only the tensors that TMA-fed GEMMs
+// consume (h sequence, y, dP, dGn) are row-major and leave through a swizzled staging tile + TMA store.
+//
+// Blocked layout of a logical [R rows, A arrays, H units] bf16 tensor (R multiple of 128):
+//     vec16(R, a, u) = ((R/128 * A + a) * (H/8) + u/8) * 128 + R%128        (index of a 16-byte vector)
+// i.e. for fixed (array, 8-unit group) the 128 rows of a tile are contiguous.
+#pragma once
+#include "runtime.h"
+#include "ptx.cuh"
+
+namespace ipn {
+
+constexpr int GP_ROWS = 128;                      // batch rows per CTA
+constexpr int GP_CH = 64;                         // hidden units per chunk / per k-block
+constexpr int GP_KB_BYTES = GP_ROWS * 128;        // one A k-block: 128 rows x 64 bf16 (SWIZZLE_128B)
+constexpr int GP_THREADS = 640;                   // W producer, MMA, store, A loader, 16 epilogue warps
+constexpr int GP_GATE_ARRAYS = 5;                 // saved per step: r, z, n, W_hn h + b_hn, h_prev
+
+struct GruPersistFwdDir {
+  alignas(64) CUtensorMap tmW;  // W_hh [3H, H], box 64 x 64
+  alignas(64) CUtensorMap tmH;  // hseq [(T+1)*Bt, H], box 64 x 128 (loads and stores)
+  alignas(64) CUtensorMap tmY;  // y [T*Bt, ld_y], box 64 x 128 (stores)
+  const uint4* Pblk;            // blocked [T*Bt, 3, H] input projection, nullable
+  uint4* gates;                 // blocked [T*Bt, 5, H], nullable
+  const float* b_hh;
+  const float* pvec;            // nullable
+  int reverse, y_col0, has_y, pad_;
+};
+struct GruPersistFwd {
+  GruPersistFwdDir d[2];
+  int T, H, Bt;
+  int dbg;                    // diagnostics (IPN_GPF_DBG): 1 no P loads, 2 no gate stores, 4 no gate math, 8 no W loads
+  unsigned long long* timing; // per-CTA wait-cycle counters (ipn_dbg_set_timing_buffer), normally null
+};
+
+struct GruPersistBwdDir {
+  alignas(64) CUtensorMap tmW;    // W_hh [3H, H] read MN-major: box 64 (units) x 64 (gate rows)
+  alignas(64) CUtensorMap tmDP;   // dP [T*Bt, 3H], box 64 x 128 (stores and A-operand loads)
+  alignas(64) CUtensorMap tmDG;   // dGn [T*Bt, H], box 64 x 128
+  const uint4* gates;             // blocked [T*Bt, 5, H]
+  const uint4* dYblk;             // blocked [T*Bt, 1, H] (mask already applied), nullable
+  float4* carry;                  // blocked fp32 [Bt, H]: dh * z handed to the next (earlier) step
+  const float* dh_n;              // nullable, row-major fp32 [Bt, ld_dhn]
+  long long ld_dhn;
+  void* dh0;                      // nullable
+  long long ld_dh0;
+  const void* h0;                 // row-major bf16 [Bt, H] (SELU' of the initial state)
+  int dh0_dt, dh0_selu, reverse, pad_;
+};
+struct GruPersistBwd {
+  GruPersistBwdDir d[2];
+  int T, H, Bt, pad_;
+};
+
+}  // namespace ipn

@@ -159,6 +159,24 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, unsigned long long inner, 
   return IPN_OK;
 }
 
+int get_tensor_map_3d(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                      long long ld1, long long ld2, unsigned box1, unsigned box2) {
+  IPN_REQUIRE(ptr != nullptr && reinterpret_cast<uintptr_t>(ptr) % 16 == 0, IPN_ERR_ALIGN, "tensor map 3d: bad pointer %p", ptr);
+  IPN_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0, IPN_ERR_ALIGN, "tensor map 3d: strides must be multiples of 8 bf16");
+  IPN_REQUIRE(d0 > 0 && d1 > 0 && d2 > 0 && box1 > 0 && box1 <= 256 && box2 > 0 && box2 <= 256, IPN_ERR_ARG, "tensor map 3d: bad dims");
+  EncodeTiledFn fn = get_encode_fn();
+  IPN_REQUIRE(fn != nullptr, IPN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
+  cuuint32_t box[3] = {64, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IPN_REQUIRE(r == CUDA_SUCCESS, IPN_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return IPN_OK;
+}
+
 }  // namespace ipn
 
 extern "C" {

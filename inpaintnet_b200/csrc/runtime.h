@@ -25,6 +25,10 @@ struct ProfScope {
 int get_tensor_map(CUtensorMap* out, const void* ptr, unsigned long long inner, unsigned long long outer,
                    long long ld, unsigned box_outer);
 
+// bf16, 3-D, SWIZZLE_128B tensor map: dims {d0 (contiguous), d1, d2}, strides ld1/ld2 in elements, box {64, box1, box2}.
+int get_tensor_map_3d(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                      long long ld1, long long ld2, unsigned box1, unsigned box2);
+
 #define IPN_LAUNCH_CHECK()                                                                        \
   do {                                                                                            \
     cudaError_t _e = cudaGetLastError();                                                          \

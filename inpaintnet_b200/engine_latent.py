@@ -22,7 +22,7 @@ def bigru2_forward(arena, pfx, prec, H, T, B, x, hseq, training, p_drop, need_gr
     dev, act = hseq.device, prec.tdt
     drop = training and p_drop > 0.0
     scale = 1.0 / (1.0 - p_drop) if drop else 1.0
-    gates = torch.empty(2, 2, T * B, 4 * H, dtype=act, device=dev) if need_grad else None
+    gates = torch.empty(2, 2, T * B, ops.gates_cols(H), dtype=act, device=dev) if need_grad else None
     y0 = torch.empty(T * B, 2 * H, dtype=act, device=dev)
     y1 = torch.empty(T * B, 2 * H, dtype=act, device=dev) if want_y1 else None
     mask0 = NOISE.keep_mask(arena, (T * B, 2 * H), p_drop, dev) if drop else None
@@ -55,8 +55,8 @@ def bigru2_forward(arena, pfx, prec, H, T, B, x, hseq, training, p_drop, need_gr
         dirs.append(ops.gru_dir(arena.w(prec, pfx + "weight_hh_l0" + s)[0], arena.fptr(pfx + "bias_hh_l0" + s),
                                 hseq[0, d].data_ptr(), gates=gates[0, d].data_ptr() if need_grad else 0, reverse=d,
                                 y_col0=d * H, **src, **fin(0, d)))
-    ops.gru_layer_fwd(prec, T, B, H, dirs, y=y0.data_ptr(), ld_y=2 * H, mask=mask0.data_ptr() if drop else 0, ld_mask=2 * H,
-                      mask_scale=scale)
+    pk0 = ops.gru_layer_fwd(prec, T, B, H, dirs, y=y0.data_ptr(), ld_y=2 * H, mask=mask0.data_ptr() if drop else 0,
+                            ld_mask=2 * H, mask_scale=scale)
     P1 = torch.empty(2, T * B, 3 * H, dtype=act, device=dev)
     for d, s in enumerate(SFX):
         _lin(prec, y0.data_ptr(), 2 * H, T * B, 2 * H, arena.w(prec, pfx + "weight_ih_l1" + s), 3 * H, P1[d].data_ptr(),
@@ -64,8 +64,8 @@ def bigru2_forward(arena, pfx, prec, H, T, B, x, hseq, training, p_drop, need_gr
     dirs = [ops.gru_dir(arena.w(prec, pfx + "weight_hh_l1" + s)[0], arena.fptr(pfx + "bias_hh_l1" + s),
                         hseq[1, d].data_ptr(), gates=gates[1, d].data_ptr() if need_grad else 0, P=P1[d].data_ptr(),
                         ldP=3 * H, reverse=d, y_col0=d * H, **fin(1, d)) for d, s in enumerate(SFX)]
-    ops.gru_layer_fwd(prec, T, B, H, dirs, y=y1.data_ptr() if want_y1 else 0, ld_y=2 * H)
-    saved = dict(T=T, B=B, H=H, hseq=hseq, gates=gates, y0=y0, mask0=mask0, scale=scale, x=x) if need_grad else None
+    pk1 = ops.gru_layer_fwd(prec, T, B, H, dirs, y=y1.data_ptr() if want_y1 else 0, ld_y=2 * H)
+    saved = dict(T=T, B=B, H=H, hseq=hseq, gates=gates, y0=y0, mask0=mask0, scale=scale, x=x, pk=(pk0, pk1)) if need_grad else None
     return y1, saved
 
 
@@ -91,7 +91,7 @@ def bigru2_backward(arena, pfx, prec, saved, dY1=None, dh_n=None, dh0=None):
                             dP[d].data_ptr(), dGn[d].data_ptr(), reverse=d, y_col0=d * H, **extra(1, d))
             for d, s in enumerate(SFX)]
     ops.gru_layer_bwd(prec, T, B, H, dirs, ws.data_ptr(), dY=dY1[0] if dY1 is not None else 0,
-                      ld_dy=dY1[1] if dY1 is not None else 0)
+                      ld_dy=dY1[1] if dY1 is not None else 0, persistent=saved["pk"][1])
     for d, s in enumerate(SFX):
         hprev = hseq[1, d].data_ptr() + (es * B * H if d == 1 else 0)
         _gru_wgrads(arena, prec, pfx, "_l1" + s, H, T * B, dP[d].data_ptr(), dGn[d].data_ptr(), hprev, X=y0.data_ptr(),
@@ -105,7 +105,8 @@ def bigru2_backward(arena, pfx, prec, saved, dY1=None, dh_n=None, dh0=None):
                             dP[d].data_ptr(), dGn[d].data_ptr(), reverse=d, y_col0=d * H, **extra(0, d))
             for d, s in enumerate(SFX)]
     ops.gru_layer_bwd(prec, T, B, H, dirs, ws.data_ptr(), dY=dY0.data_ptr(), ld_dy=2 * H,
-                      mask=mask0.data_ptr() if mask0 is not None else 0, ld_mask=2 * H, mask_scale=saved["scale"])
+                      mask=mask0.data_ptr() if mask0 is not None else 0, ld_mask=2 * H, mask_scale=saved["scale"],
+                      persistent=saved["pk"][0])
     x = saved["x"]
     for d, s in enumerate(SFX):
         hprev = hseq[0, d].data_ptr() + (es * B * H if d == 1 else 0)

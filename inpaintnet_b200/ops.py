@@ -75,6 +75,19 @@ def gemm(core, in_dt, M, N, segs, out, out_dt, ld_out, bias=0, act=ACT_NONE, alp
     L.check(lib().ipn_gemm(C.byref(g), stream()))
 
 
+def gates_cols(H):
+    """elements per (timestep, row) of the opaque `gates` buffer of ipn_gru_layer_fwd/bwd"""
+    return lib().ipn_gru_gates_cols(H)
+
+
+def _workspace(nbytes):
+    """Transient device workspace of a persistent layer kernel (stream-ordered: the caching allocator reuses
+    the block only for later work on the same stream)."""
+    if nbytes <= 0:
+        return None
+    return torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+
+
 def gru_dir(w_hh, b_hh, hseq, gates=0, P=0, ldP=0, P_bcast=0, table=0, ld_table=0, tok=0, pvec=0, reverse=0,
             y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0):
     d = L.GruDir()
@@ -86,7 +99,7 @@ def gru_dir(w_hh, b_hh, hseq, gates=0, P=0, ldP=0, P_bcast=0, table=0, ld_table=
 
 
 def gru_layer_fwd(prec, T, B_total, H, dirs, y=0, ld_y=0, mask=0, ld_mask=0, mask_scale=1.0, final_out=0,
-                  final_dt=F32, ld_final=0, row0=0, nrows=None, s_begin=0, s_end=None):
+                  final_dt=F32, ld_final=0, row0=0, nrows=None, s_begin=0, s_end=None, persistent=True):
     p = L.GruLayer()
     p.core, p.act_dt, p.T, p.B_total, p.H = prec.core, prec.act, T, B_total, H
     p.row0, p.nrows = row0, B_total if nrows is None else nrows
@@ -96,7 +109,10 @@ def gru_layer_fwd(prec, T, B_total, H, dirs, y=0, ld_y=0, mask=0, ld_mask=0, mas
         p.dir[i] = d
     p.y, p.ld_y, p.mask, p.ld_mask, p.mask_scale = y or None, ld_y, mask or None, ld_mask, mask_scale
     p.final_out, p.final_dt, p.ld_final = final_out or None, final_dt, ld_final
+    ws = _workspace(lib().ipn_gru_layer_fwd_ws_bytes(C.byref(p))) if persistent else None
+    p.ws, p.ws_bytes = (ws.data_ptr(), ws.numel()) if ws is not None else (None, 0)
     L.check(lib().ipn_gru_layer_fwd(C.byref(p), stream()))
+    return ws is not None
 
 
 def gru_bwd_dir(w_hh, hseq, gates, dP, dGn, dh_n=0, ld_dhn=0, dh0=0, dh0_dt=F32, ld_dh0=0, dh0_selu=0, reverse=0,
@@ -109,13 +125,18 @@ def gru_bwd_dir(w_hh, hseq, gates, dP, dGn, dh_n=0, ld_dhn=0, dh0=0, dh0_dt=F32,
 
 
 def gru_layer_bwd(prec, T, B_total, H, dirs, dhz_ws, dY=0, ld_dy=0, mask=0, ld_mask=0, mask_scale=1.0, row0=0,
-                  nrows=None):
+                  nrows=None, persistent=False):
+    """persistent: what the matching gru_layer_fwd call returned (the persistent forward kernel writes the
+    saved-gates buffer in its own blocked layout)."""
     p = L.GruLayerBwd()
     p.core, p.act_dt, p.T, p.B_total, p.H = prec.core, prec.act, T, B_total, H
     p.row0, p.nrows, p.ndir = row0, B_total if nrows is None else nrows, len(dirs)
     for i, d in enumerate(dirs):
         p.dir[i] = d
     p.dY, p.ld_dy, p.mask, p.ld_mask, p.mask_scale, p.dhz_ws = dY or None, ld_dy, mask or None, ld_mask, mask_scale, dhz_ws
+    p.gates_persist = 1 if persistent else 0
+    ws = _workspace(lib().ipn_gru_layer_bwd_ws_bytes(C.byref(p))) if persistent else None
+    p.ws, p.ws_bytes = (ws.data_ptr(), ws.numel()) if ws is not None else (None, 0)
     L.check(lib().ipn_gru_layer_bwd(C.byref(p), stream()))
 
 

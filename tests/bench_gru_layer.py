@@ -12,7 +12,7 @@ whh = [torch.randn(3 * H, H, device=dev).mul(0.04).bfloat16() for _ in range(2)]
 bhh = [torch.zeros(3 * H, device=dev) for _ in range(2)]
 P = torch.randn(2, T * B, 3 * H, device=dev).bfloat16()
 hseq = torch.zeros(2, (T + 1) * B, H, device=dev, dtype=torch.bfloat16)
-gates = torch.empty(2, T * B, 4 * H, device=dev, dtype=torch.bfloat16)
+gates = torch.empty(2, T * B, ops.gates_cols(H), device=dev, dtype=torch.bfloat16)
 y = torch.empty(T * B, 2 * H, device=dev, dtype=torch.bfloat16)
 mask = (torch.rand(T * B, 2 * H, device=dev) > 0.5).to(torch.uint8)
 dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), gates=gates[d].data_ptr(), P=P[d].data_ptr(),

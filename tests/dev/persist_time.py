@@ -1,0 +1,33 @@
+"""dev: timing + wait-cycle counters of the persistent GRU forward kernel (env IPN_GPF_DBG selects ablations)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from inpaintnet_b200 import ops
+from inpaintnet_b200.ops import Precision, F32
+
+DEV = "cuda"
+prec = Precision("bf16")
+H, B, T, ndir = 512, int(os.environ.get("B", 4096)), 24, int(os.environ.get("NDIR", 2))
+g = torch.Generator().manual_seed(0)
+s = 1.0 / H ** 0.5
+whh = [((torch.rand(3 * H, H, generator=g) * 2 - 1) * s).to(DEV).bfloat16().contiguous() for _ in range(ndir)]
+bhh = [((torch.rand(3 * H, generator=g) * 2 - 1) * s).to(DEV) for _ in range(ndir)]
+P = torch.randn(ndir, T * B, 3 * H, device=DEV).bfloat16()
+hseq = torch.zeros(ndir, (T + 1) * B, H, dtype=torch.bfloat16, device=DEV)
+gates = torch.zeros(ndir, T * B, ops.gates_cols(H), dtype=torch.bfloat16, device=DEV)
+y = torch.zeros(T * B, ndir * H, dtype=torch.bfloat16, device=DEV)
+dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), gates=gates[d].data_ptr(),
+                    P=P[d].data_ptr(), ldP=3 * H, reverse=d, y_col0=d * H) for d in range(ndir)]
+ncta = (B // 128) * ndir
+timing = torch.zeros(ncta * 16, dtype=torch.int64, device=DEV)
+ops.lib().ipn_dbg_set_timing_buffer(timing.data_ptr())
+ops.prof_enable(True)
+for _ in range(4):
+    ops.gru_layer_fwd(prec, T, B, H, dirs, y=y.data_ptr(), ld_y=ndir * H)
+rep = ops.prof_report()
+t = timing.view(ncta, 16).float().mean(0).cpu().tolist()
+names = ["mma_total", "mma_wait_tmem_empty", "mma_wait_a_full", "mma_wait_w_full", "st_wait_ready", "st_store_time",
+         "al_wait_a_free", "al_wait_h_stored", "epi_total", "epi_wait_tmem_full", "epi_wait_stg_free"]
+print("dbg=%s B=%d ndir=%d" % (os.environ.get("IPN_GPF_DBG", "0"), B, ndir),
+      {k: "%.3f ms (%d launches)" % (v["ms"] / v["launches"], v["launches"]) for k, v in rep.items()})
+print("  per-step kcycles:", {n: round(v / T / 1000, 1) for n, v in zip(names, t)})

@@ -23,7 +23,8 @@ def _to_dev(t, prec):
 
 
 @pytest.mark.parametrize("prec_name,H,B,T", [("fp32", 32, 5, 7), ("fp32", 40, 70, 3), ("bf16", 64, 130, 6),
-                                              ("bf16", 512, 256, 4), ("bf16", 72, 9, 5)])
+                                              ("bf16", 512, 256, 4), ("bf16", 72, 9, 5), ("bf16", 128, 384, 5),
+                                              ("bf16", 256, 128, 3)])
 def test_gru_layer_fwd_bwd_bidirectional(prec_name, H, B, T):
     prec = Precision(prec_name)
     I = 24
@@ -65,14 +66,15 @@ def test_gru_layer_fwd_bwd_bidirectional(prec_name, H, B, T):
     hseq = torch.zeros(2, (T + 1) * B, H, dtype=prec.tdt, device=DEV)
     hseq[0, :B] = _to_dev(h0[0], prec)
     hseq[1, T * B:] = _to_dev(h0[1], prec)
-    gates = torch.empty(2, T * B, 4 * H, dtype=prec.tdt, device=DEV)
+    gates = torch.empty(2, T * B, ops.gates_cols(H), dtype=prec.tdt, device=DEV)
     y = torch.empty(T * B, 2 * H, dtype=prec.tdt, device=DEV)
     mask = keep.transpose(0, 1).reshape(T * B, 2 * H).to(torch.uint8).to(DEV).contiguous()
     fin = torch.empty(B, 2 * H, dtype=torch.float32, device=DEV)
     dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), gates=gates[d].data_ptr(),
                         P=P[d].data_ptr(), ldP=3 * H, reverse=d, y_col0=d * H, final_col0=d * H) for d in range(2)]
-    ops.gru_layer_fwd(prec, T, B, H, dirs, y=y.data_ptr(), ld_y=2 * H, mask=mask.data_ptr(), ld_mask=2 * H,
-                      mask_scale=1 / (1 - p_drop), final_out=fin.data_ptr(), final_dt=F32, ld_final=2 * H)
+    pk = ops.gru_layer_fwd(prec, T, B, H, dirs, y=y.data_ptr(), ld_y=2 * H, mask=mask.data_ptr(), ld_mask=2 * H,
+                           mask_scale=1 / (1 - p_drop), final_out=fin.data_ptr(), final_dt=F32, ld_final=2 * H)
+    assert pk == (prec_name == "bf16" and H % 64 == 0 and H <= 512 and B % 128 == 0)
     torch.cuda.synchronize()
     tol = dict(atol=2e-5, rtol=1e-4) if prec_name == "fp32" else dict(atol=3e-2, rtol=3e-2)
     y_lib = y.float().cpu().view(T, B, 2 * H).transpose(0, 1)
@@ -91,7 +93,7 @@ def test_gru_layer_fwd_bwd_bidirectional(prec_name, H, B, T):
                           dh_n=dhn[d].data_ptr(), ld_dhn=H, dh0=dh0[d].data_ptr(), dh0_dt=F32, ld_dh0=H, reverse=d,
                           y_col0=d * H) for d in range(2)]
     ops.gru_layer_bwd(prec, T, B, H, bd, ws.data_ptr(), dY=dY.data_ptr(), ld_dy=2 * H, mask=mask.data_ptr(),
-                      ld_mask=2 * H, mask_scale=1 / (1 - p_drop))
+                      ld_mask=2 * H, mask_scale=1 / (1 - p_drop), persistent=pk)
     # hoisted weight gradients
     for d in range(2):
         gW_hh = torch.zeros(3 * H, H, device=DEV)
