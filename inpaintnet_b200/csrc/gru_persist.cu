@@ -6,52 +6,6 @@
 namespace ipn {
 
 // ---------------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 x = __bfloat1622float2(h2[k]);
-    f[2 * k] = x.x;
-    f[2 * k + 1] = x.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-  return u;
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 u;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
-  return u;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& u) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
-}
-// streaming 16-byte global accesses (each element is touched once per step)
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-  uint4 u;
-  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-               : "l"(p));
-  return u;
-}
-__device__ __forceinline__ void stg_stream(uint4* p, const uint4& u) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
-               : "memory");
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-
-// ---------------------------------------------------------------------------------------------
 // input-projection prep: blocked bf16 pre-activation input of every gate, everything that does not depend
 // on h folded in:   r, z: 0.5 * (P + table[tok] + pvec + b_hh)   (sigmoid(x) = 0.5 tanh(0.5 x) + 0.5)
 //                   n   :        P + table[tok] + pvec            (b_hn stays inside r * (.))
@@ -136,18 +90,6 @@ __global__ void gru_mask_y_kernel(__nv_bfloat16* y, long long ld_y, const unsign
 // ---------------------------------------------------------------------------------------------
 // the persistent forward kernel
 // ---------------------------------------------------------------------------------------------
-extern unsigned long long* g_dbg_timing;
-
-// mbarrier wait that adds the waited cycles to a counter when diagnostics are on
-__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
-  if (on) {
-    const long long t0 = clock64();
-    ptx::mbar_wait(bar, parity);
-    acc += clock64() - t0;
-  } else {
-    ptx::mbar_wait(bar, parity);
-  }
-}
 constexpr int GPF_W_BYTES = 3 * GP_CH * 128;  // one (chunk, k-block) of W_hh: 3 gates x 64 rows x 64 bf16 = 24 KB
 constexpr int GPF_W_RING = 3 * GPF_W_BYTES;   // shared memory of the W ring (3 stages; 6 half-size stages per CTA of a pair)
 constexpr int GPF_NBAR = 48;

@@ -15,6 +15,7 @@
 #pragma once
 #include "runtime.h"
 #include "ptx.cuh"
+#include <cuda_bf16.h>
 
 namespace ipn {
 
@@ -42,22 +43,88 @@ struct GruPersistFwd {
 };
 
 struct GruPersistBwdDir {
-  alignas(64) CUtensorMap tmW;    // W_hh [3H, H] read MN-major: box 64 (units) x 64 (gate rows)
+  alignas(64) CUtensorMap tmW;    // W_hh [3H, H] as {64 n, 3H k, H/64 n-blocks}: box {64, 64, n-blocks per stage} (MN-major B)
   alignas(64) CUtensorMap tmDP;   // dP [T*Bt, 3H], box 64 x 128 (stores and A-operand loads)
   alignas(64) CUtensorMap tmDG;   // dGn [T*Bt, H], box 64 x 128
   const uint4* gates;             // blocked [T*Bt, 5, H]
   const uint4* dYblk;             // blocked [T*Bt, 1, H] (mask already applied), nullable
-  float4* carry;                  // blocked fp32 [Bt, H]: dh * z handed to the next (earlier) step
   const float* dh_n;              // nullable, row-major fp32 [Bt, ld_dhn]
   long long ld_dhn;
   void* dh0;                      // nullable
   long long ld_dh0;
-  const void* h0;                 // row-major bf16 [Bt, H] (SELU' of the initial state)
+  const __nv_bfloat16* h0;        // row-major [Bt, H]: the initial state (SELU' of it when dh0_selu)
   int dh0_dt, dh0_selu, reverse, pad_;
 };
 struct GruPersistBwd {
   GruPersistBwdDir d[2];
-  int T, H, Bt, pad_;
+  int T, H, Bt;
+  int nbs;                        // 64-wide n-blocks of W_hh staged per CTA and stage
+  int dbg;
+  int pad_;
+  unsigned long long* timing;
 };
+
+}  // namespace ipn
+
+namespace ipn {
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 x = __bfloat1622float2(h2[k]);
+    f[2 * k] = x.x;
+    f[2 * k + 1] = x.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return u;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& u) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+// streaming 16-byte global accesses (each element is touched once per step)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 u;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "l"(p));
+  return u;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& u) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+               : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+
+extern unsigned long long* g_dbg_timing;
+
+// mbarrier wait that adds the waited cycles to a counter when diagnostics are on
+__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+  if (on) {
+    const long long t0 = clock64();
+    ptx::mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    ptx::mbar_wait(bar, parity);
+  }
+}
 
 }  // namespace ipn
