@@ -182,12 +182,16 @@ typedef struct {
   long long ld_final;
   void* ws; /* nullable */
   long long ws_bytes;
+  int gates_blocked; /* per-step kernels only: write `gates` in the persistent kernels' private layout so that the
+                        backward pass can run ipn_gru_layer_bwd with gates_persist = 1 (needs ipn_gru_persist_eligible) */
 } IpnGruLayer;
 int ipn_gru_layer_fwd(const IpnGruLayer* p, void* stream);
 /* bytes of workspace with which ipn_gru_layer_fwd runs the persistent kernel; 0 = not eligible */
 long long ipn_gru_layer_fwd_ws_bytes(const IpnGruLayer* p);
 /* elements per (timestep, batch row) of the `gates` buffer */
 int ipn_gru_gates_cols(int H);
+/* 1 when a layer of this shape can use the persistent kernels' saved-gates layout */
+int ipn_gru_persist_eligible(int core, int act_dt, int B_total, int H);
 
 /* GRU layer backward (BPTT, reverse-time).  replaces the autograd of torch.nn.GRU reached from
  * utils/trainer.py:150 (loss.backward()).  Produces, time-ordered: dP [T*B_total,3H] (gradient wrt
@@ -344,6 +348,7 @@ typedef struct {
   int use_maps;       /* 0: row b of tick t -> weights + (b*24 + t)*V, samples + b*24 + t */
   IpnRowMap wmap;     /* else: weights + wmap(b) + t*V   and   samples + smap(b) + t */
   IpnRowMap smap;
+  int gates_blocked;  /* see IpnGruLayer.gates_blocked */
 } IpnTickDecode;
 int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream);
 

@@ -41,7 +41,7 @@ class GruLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B_total", i32), ("H", i32), ("row0", i32),
                 ("nrows", i32), ("s_begin", i32), ("s_end", i32), ("ndir", i32), ("dir", GruDir * 2), ("y", vp),
                 ("ld_y", ll), ("mask", vp), ("ld_mask", ll), ("mask_scale", f32), ("final_out", vp),
-                ("final_dt", i32), ("ld_final", ll), ("ws", vp), ("ws_bytes", ll)]
+                ("final_dt", i32), ("ld_final", ll), ("ws", vp), ("ws_bytes", ll), ("gates_blocked", i32)]
 
 
 class GruBwdDir(C.Structure):
@@ -83,7 +83,7 @@ class TickDecode(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("B", i32), ("H", i32), ("V", i32), ("l0", GruDir), ("l1", GruDir),
                 ("yt0", vp), ("yt1", vp), ("mask", vp), ("mask_scale", f32), ("w_ih1", vp), ("b_ih1", vp),
                 ("Pt1", vp), ("w_v", vp), ("b_v", vp), ("weights", vp), ("samples", vp), ("tokprev", vp),
-                ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap)]
+                ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap), ("gates_blocked", i32)]
 
 
 STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
@@ -105,6 +105,7 @@ SYMBOLS = {
     "ipn_gru_layer_fwd_ws_bytes": (ll, [C.POINTER(GruLayer)]),
     "ipn_gru_layer_bwd_ws_bytes": (ll, [C.POINTER(GruLayerBwd)]),
     "ipn_gru_gates_cols": (i32, [i32]),
+    "ipn_gru_persist_eligible": (i32, [i32, i32, i32, i32]),
     "ipn_lstm_layer_fwd": (i32, [C.POINTER(LstmLayer), vp]),
     "ipn_lstm_layer_bwd": (i32, [C.POINTER(LstmLayerBwd), vp]),
     "ipn_tokens_time_major": (i32, [vp, i32, i32, i32, vp, vp, vp]),

@@ -18,6 +18,7 @@ extern "C" int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream) {
   L0.core = p->core; L0.act_dt = dt; L0.T = 6; L0.B_total = (int)B4; L0.H = H; L0.ndir = 1;
   L0.dir[0] = p->l0;
   L0.dir[0].tok = p->tokprev;
+  L0.gates_blocked = p->gates_blocked;
   L0.y = p->yt0; L0.ld_y = H; L0.mask = p->mask; L0.ld_mask = H; L0.mask_scale = p->mask_scale;
   IpnGruLayer L1 = L0;
   L1.dir[0] = p->l1;

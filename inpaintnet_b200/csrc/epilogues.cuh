@@ -149,6 +149,7 @@ struct GruFwdParams {
     const void* h_prev;  // slot base [B_total, H]
     void* h_out;         // slot base
     void* gates;         // [T*B_total, 4H] base, nullable
+    int gates_blocked;   // write the blocked 5-array layout of the persistent kernels instead (gru_persist.cuh)
     void* y;
     long long ld_y;
     int y_col0;
@@ -327,9 +328,16 @@ struct EpiGruFwdT {
         const long long R = p.row0 + row0 + i, TR = p.trow + R;
         st_t<DT>(p.h_out, R * H + col, h, dt);
         if (p.gates != nullptr) {
-          const long long go = TR * 4 * H + col;
-          st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
-          st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
+          if (p.gates_blocked) {
+            const long long gs = (long long)H * 128;
+            const long long go = ((((TR >> 7) * 5) * (H >> 3) + (col >> 3)) * 128 + (TR & 127)) * 8 + (col & 7);
+            st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + gs, z, dt); st_t<DT>(p.gates, go + 2 * gs, n, dt);
+            st_t<DT>(p.gates, go + 3 * gs, hn, dt); st_t<DT>(p.gates, go + 4 * gs, q.hp[i], dt);
+          } else {
+            const long long go = TR * 4 * H + col;
+            st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
+            st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
+          }
         }
         if (p.y != nullptr) st_t<DT>(p.y, TR * p.ld_y + p.y_col0 + col, ((q.mask_bits >> i) & 1u) ? h * p.mask_scale_eff() : 0.f, dt);
         if (p.final_out != nullptr) st_act(p.final_out, R * p.ld_final + p.final_col0 + col, h, p.final_dt);
@@ -390,9 +398,16 @@ struct EpiGruFwdT {
       if (i < nv && !(p.dbg & 2)) {
         st_t<DT>(p.h_out, R[i] * H + col, h, dt);
         if (p.gates != nullptr) {
-          const long long go = TR[i] * 4 * H + col;
-          st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
-          st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
+          if (p.gates_blocked) {
+            const long long gs = (long long)H * 128;
+            const long long go = ((((TR[i] >> 7) * 5) * (H >> 3) + (col >> 3)) * 128 + (TR[i] & 127)) * 8 + (col & 7);
+            st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + gs, z, dt); st_t<DT>(p.gates, go + 2 * gs, n, dt);
+            st_t<DT>(p.gates, go + 3 * gs, hn, dt); st_t<DT>(p.gates, go + 4 * gs, hp[i], dt);
+          } else {
+            const long long go = TR[i] * 4 * H + col;
+            st_t<DT>(p.gates, go, r, dt); st_t<DT>(p.gates, go + H, z, dt);
+            st_t<DT>(p.gates, go + 2 * H, n, dt); st_t<DT>(p.gates, go + 3 * H, hn, dt);
+          }
         }
         if (p.y != nullptr) st_t<DT>(p.y, TR[i] * p.ld_y + p.y_col0 + col, h * mk[i], dt);
         if (p.final_out != nullptr) st_act(p.final_out, R[i] * p.ld_final + p.final_col0 + col, h, p.final_dt);

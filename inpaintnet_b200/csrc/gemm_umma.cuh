@@ -239,31 +239,38 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && nchunks > 0) {
+    // The whole warp runs the loop (warp-uniform descriptor arithmetic); one elected lane issues.
+    if (nchunks > 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(UMMA_BC, BR, Cfg::TW ? 1 : 0, Cfg::TX ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t smem_u = ptx::smem_u32(smem);
+      const uint64_t dw_base = Cfg::TW ? ptx::make_smem_desc(smem_u, 8192, 1024) : ptx::make_smem_desc(smem_u, 16, 1024);
+      const uint64_t dx_base = Cfg::TX ? ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 8192, 1024)
+                                       : ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 16, 1024);
+      constexpr uint32_t W_KK = (Cfg::TW ? 2048 : 32) >> 4, X_KK = (Cfg::TX ? 2048 : 32) >> 4;
       for (int kc = 0; kc < nchunks; ++kc) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sw = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sx = sw + Cfg::W_BYTES;
+        const uint64_t so = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < UMMA_BK / 16; ++kk) {
-          const uint64_t dx = Cfg::TX ? ptx::make_smem_desc(sx + kk * 2048, 8192, 1024)
-                                      : ptx::make_smem_desc(sx + kk * 32, 16, 1024);
+          for (int kk = 0; kk < UMMA_BK / 16; ++kk) {
+            const uint64_t dx = dx_base + so + (uint64_t)(kk * X_KK);
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const uint64_t dw = Cfg::TW ? ptx::make_smem_desc(sw + g * 16384 + kk * 2048, 8192, 1024)
-                                        : ptx::make_smem_desc(sw + g * 16384 + kk * 32, 16, 1024);
-            ptx::umma_bf16(tmem_base + (uint32_t)(g * BR), dw, dx, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            for (int g = 0; g < G; ++g) {
+              const uint64_t dw = dw_base + so + (uint64_t)(g * (16384 >> 4) + kk * W_KK);
+              ptx::umma_bf16(tmem_base + (uint32_t)(g * BR), dw, dx, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            }
           }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
         }
-        ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(tmem_full_bar);
-      dbg_stamp<Epi>(P.epi, 3);  // all MMAs issued
+      if (ptx::elect_one()) ptx::umma_commit(tmem_full_bar);
+      __syncwarp();
+      if (lane == 0) dbg_stamp<Epi>(P.epi, 3);  // all MMAs issued
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================

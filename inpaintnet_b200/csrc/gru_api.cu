@@ -56,6 +56,12 @@ extern "C" long long ipn_gru_layer_bwd_ws_bytes(const IpnGruLayerBwd* L) {
   return gru_persist_bwd_ws_bytes(L);
 }
 extern "C" int ipn_gru_gates_cols(int H) { return 5 * H; }
+extern "C" int ipn_gru_persist_eligible(int core, int act_dt, int B_total, int H) {
+  IpnGruLayerBwd L;
+  memset(&L, 0, sizeof(L));
+  L.core = core; L.act_dt = act_dt; L.T = 1; L.B_total = B_total; L.H = H; L.row0 = 0; L.nrows = B_total; L.ndir = 0;
+  return gru_persist_bwd_shape_ok(&L) ? 1 : 0;
+}
 
 namespace ipn { unsigned long long* g_dbg_timing = nullptr; }
 extern "C" void ipn_dbg_set_timing_buffer(void* dev_ptr) { g_dbg_timing = reinterpret_cast<unsigned long long*>(dev_ptr); }
@@ -75,6 +81,8 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     IPN_REQUIRE(!D.table || D.tok, IPN_ERR_ARG, "gru_layer_fwd: table without tokens");
   }
   if (L->ws != nullptr && gru_persist_fwd_shape_ok(L)) return gru_persist_fwd(L, L->ws, L->ws_bytes, stream);
+  IPN_REQUIRE(!L->gates_blocked || (L->core == IPN_CORE_UMMA && Bt % 128 == 0 && H % 8 == 0), IPN_ERR_ARG,
+              "gru_layer_fwd: gates_blocked needs the tcgen05 core and B_total %% 128 == 0");
 
   static const int dbg_epi = getenv("IPN_DBG_EPI") ? atoi(getenv("IPN_DBG_EPI")) : 0;
   static const int gru_br = getenv("IPN_GRU_BR") ? atoi(getenv("IPN_GRU_BR")) : 128;
@@ -88,6 +96,7 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     e.h_prev = slot_ptr(D.hseq, in_slot, Bt, H, dt);
     e.h_out = const_cast<char*>(slot_ptr(D.hseq, out_slot, Bt, H, dt));
     e.gates = D.gates;
+    e.gates_blocked = L->gates_blocked;
     e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = D.y_col0; e.mask = L->mask; e.ld_mask = L->ld_mask;
     e.mask_scale = L->mask_scale;
     const bool last = (s == T - 1);

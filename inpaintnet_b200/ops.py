@@ -80,6 +80,10 @@ def gates_cols(H):
     return lib().ipn_gru_gates_cols(H)
 
 
+def persist_eligible(prec, B_total, H):
+    return bool(lib().ipn_gru_persist_eligible(prec.core, prec.act, B_total, H))
+
+
 def _workspace(nbytes):
     """Transient device workspace of a persistent layer kernel (stream-ordered: the caching allocator reuses
     the block only for later work on the same stream)."""
@@ -160,8 +164,9 @@ def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP
 
 
 def tick_decode_argmax(prec, B, H, V, l0, l1, yt0, yt1, mask, mask_scale, w_ih1, b_ih1, Pt1, w_v, b_v, weights,
-                       samples, tokprev, wmap=None, smap=None):
+                       samples, tokprev, wmap=None, smap=None, gates_blocked=False):
     p = L.TickDecode()
+    p.gates_blocked = 1 if gates_blocked else 0
     if wmap is not None:
         p.use_maps = 1
         p.wmap.g1, p.wmap.g2, p.wmap.s1, p.wmap.s2, p.wmap.s3 = wmap
