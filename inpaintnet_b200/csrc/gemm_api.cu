@@ -1,5 +1,6 @@
 // ipn_gemm: universal GEMM + fused epilogue (see include/inpaintnet_b200.h).
 #include "launch.cuh"
+#include <stdlib.h>
 
 namespace ipn {
 
@@ -26,6 +27,7 @@ static int fill_linear_epi(EpiLinear::Params& e, const IpnGemm* g) {
 // API operands: A = activations [M,K] (output rows), B = weights [N,K] (output columns).
 template <int BR, bool TW, bool TX>
 static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
+  static const int persist = getenv("IPN_GEMM_PERSIST") ? atoi(getenv("IPN_GEMM_PERSIST")) : 1;
   using Cfg = UmmaCfg<1, BR, TW, TX>;
   UmmaBatch<EpiLinear> b;
   memset(&b, 0, sizeof(b));
@@ -42,8 +44,9 @@ static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
     IPN_PROPAGATE(fill_umma_seg(P.seg[s], x, w, sg.K, BR));
   }
   fill_linear_epi(P.epi, g);
-  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream,
-                                     TX ? "gemm_umma_tn_wgrad" : (TW ? "gemm_umma_nn_dgrad" : "gemm_umma_nt"));
+  const char* tag = TX ? "gemm_umma_tn_wgrad" : (TW ? "gemm_umma_nn_dgrad" : "gemm_umma_nt");
+  if (persist) return launch_umma_persist<UmmaPCfg<BR, TW, TX>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
+  return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream, tag);
 }
 
 static int pick_split_k(const IpnGemm* g, int tile_m, int tile_n, int bk) {

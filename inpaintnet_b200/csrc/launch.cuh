@@ -90,6 +90,29 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
   return IPN_OK;
 }
 
+template <class Cfg, class Epi>
+int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
+                        const char* tag = "umma") {
+  ProfScope prof(tag, batch_flops(batch.p, nprob, Epi::G), 0.0, stream);
+  static bool configured = false;
+  static int sms = 148;
+  auto kern = umma_gemm_persist_kernel<Cfg, Epi>;
+  if (!configured) {
+    IPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int ntx = cdiv(maxN, UMMA_BC), nty = cdiv(maxM, Cfg::BR);
+  const long long ntiles = (long long)ntx * nty * nprob * batch.split_k;
+  IPN_REQUIRE(ntiles < (1LL << 30), IPN_ERR_ARG, "too many tiles");
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(batch, ntx, nty, (int)ntiles);
+  IPN_LAUNCH_CHECK();
+  return IPN_OK;
+}
+
 template <class Epi>
 int launch_simt(const SimtBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
                 const char* tag = "simt") {
