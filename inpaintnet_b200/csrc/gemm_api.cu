@@ -37,15 +37,21 @@ static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
   P.M = g->M;
   P.N = g->N;
   P.gate_stride = 0;
+  // CTA pairs (256-column x BR-row tiles, X tile shared between the two SMs) when there is more than one column tile
+  const bool pair = persist == 1 && BR >= 128 && g->N > UMMA_BC;
   for (int s = 0; s < g->nseg; ++s) {
     const IpnGemmSeg& sg = g->seg[s];
     HostOperand x{sg.A, sg.lda, sg.transA, g->M, 0, 0};
     HostOperand w{sg.B, sg.ldb, sg.transB, g->N, 0, 0};
-    IPN_PROPAGATE(fill_umma_seg(P.seg[s], x, w, sg.K, BR));
+    IPN_PROPAGATE(fill_umma_seg(P.seg[s], x, w, sg.K, pair ? BR / 2 : BR));   // a pair's CTA stages half of the X rows
   }
   fill_linear_epi(P.epi, g);
   const char* tag = TX ? "gemm_umma_tn_wgrad" : (TW ? "gemm_umma_nn_dgrad" : "gemm_umma_nt");
-  if (persist) return launch_umma_persist<UmmaPCfg<BR, TW, TX>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
+  if constexpr (BR >= 128) {
+    if (pair)
+      return launch_umma_persist<UmmaPCfg<BR, TW, TX, true>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
+  }
+  if (persist) return launch_umma_persist<UmmaPCfg<BR, TW, TX, false>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
   return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream, tag);
 }
 

@@ -360,31 +360,36 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
 // mainloop), and there is no wave quantisation.  Tiles are ordered column-tile fastest so that the CTAs
 // running at the same time share the X row tile (streamed from HBM once) while W stays L2-resident.
 // =============================================================================================
-template <int BR_, bool TW_, bool TX_>
+template <int BR_, bool TW_, bool TX_, bool PAIR_ = false>
 struct UmmaPCfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int PARTS = EPI_WARPS / 4;
   static constexpr int G = 1;
-  static constexpr int BR = BR_;
+  static constexpr int BR = BR_;             // output rows of the tile (MMA N)
   static constexpr bool TW = TW_;
   static constexpr bool TX = TX_;
+  static constexpr bool PAIR = PAIR_;        // cta_group::2: the pair computes 256 output columns x BR rows,
+  static constexpr int XR = PAIR_ ? BR_ / 2 : BR_;   // each CTA stages its own W tile and HALF of the X tile
   static constexpr int W_BYTES = UMMA_BC * UMMA_BK * 2;
-  static constexpr int X_BYTES = BR_ * UMMA_BK * 2;
+  static constexpr int X_BYTES = XR * UMMA_BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
   static constexpr uint32_t TMEM_COLS = 2 * BR_ <= 32 ? 32 : 2 * BR_ <= 64 ? 64 : 2 * BR_ <= 128 ? 128 : 2 * BR_ <= 256 ? 256 : 512;
-  static_assert(BR_ % 16 == 0 && BR_ >= 16 && BR_ <= 256, "UMMA N must be a multiple of 16 in [16,256] for M=128");
-  static_assert(!TX_ || (BR_ % 64 == 0), "MN-major X needs 64-wide blocks");
+  static_assert(BR_ % 16 == 0 && BR_ >= 16 && BR_ <= 256, "UMMA N must be a multiple of 16 in [16,256]");
+  static_assert(!TX_ || (XR % 64 == 0), "MN-major X needs 64-wide blocks");
+  static_assert(!PAIR_ || BR_ % 32 == 0, "pair tiles split the X rows in two");
 };
 
+// ntx counts column tiles of 128 (PAIR: column-tile PAIRS of 256); grid.x CTAs (PAIR: clusters of 2)
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, int nty, int ntiles) {
   static_assert(Epi::G == 1, "the persistent GEMM serves single-accumulator epilogues");
   constexpr int BR = Cfg::BR, STAGES = Cfg::STAGES;
+  constexpr bool PAIR = Cfg::PAIR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -394,16 +399,23 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile stream this CTA (pair) follows
+  const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], Cfg::EPI_WARPS); }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&tmem_full[b], 1);
+        ptx::mbar_init(&tmem_empty[b], PAIR ? 2 * Cfg::EPI_WARPS : Cfg::EPI_WARPS);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    ptx::tmem_relinquish();
+    if (PAIR) { ptx::tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); ptx::tmem_relinquish(); }
   } else if (warp == 0 && lane == 0) {
     for (int pi = 0; pi < 2; ++pi) {
       if (batch.p[pi].nseg <= 0) continue;
@@ -414,10 +426,12 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (problem, k-split, column tile, row tile) and its k-chunk range
+  // tile -> (problem, k-split, column tile, row tile) and its k-chunk range.  Both CTAs of a pair derive the
+  // SAME k range (validity is decided per pair) so that their pipelines stay in lock step.
   struct Tile { int prob, c0, r0, kc_begin, kc_end, chunks_seg0; };
   auto decode = [&](int t) {
     Tile o;
@@ -426,14 +440,15 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
     o.prob = z / batch.split_k;
     const int ksplit = z - o.prob * batch.split_k;
     const UmmaProblem<Epi>& P = batch.p[o.prob];
-    o.c0 = tx * UMMA_BC;
+    const int pc0 = tx * (PAIR ? 2 * UMMA_BC : UMMA_BC);
+    o.c0 = pc0 + (int)rank * UMMA_BC;
     o.r0 = ty * BR;
     o.chunks_seg0 = (P.seg[0].K + UMMA_BK - 1) / UMMA_BK;
     const int total = o.chunks_seg0 + (P.nseg > 1 ? (P.seg[1].K + UMMA_BK - 1) / UMMA_BK : 0);
     const int per = (total + batch.split_k - 1) / batch.split_k;
     o.kc_begin = ksplit * per;
     o.kc_end = min(total, o.kc_begin + per);
-    if (o.c0 >= P.N || o.r0 >= P.M) o.kc_end = o.kc_begin;   // tile outside this problem: nothing to do
+    if (pc0 >= P.N || o.r0 >= P.M) o.kc_end = o.kc_begin;   // tile outside this problem: nothing to do
     return o;
   };
 
@@ -442,9 +457,10 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int t = worker; t < ntiles; t += nworkers) {
         const Tile ti = decode(t);
         const UmmaProblem<Epi>& P = batch.p[ti.prob];
+        const int xr0 = ti.r0 + (PAIR ? (int)rank * Cfg::XR : 0);   // this CTA's part of the X tile
         for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
           const int si = (kc >= ti.chunks_seg0) ? 1 : 0;
           const UmmaSeg& S = P.seg[si];
@@ -452,80 +468,93 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sw = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sx = sw + Cfg::W_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * (PAIR ? 2 : 1));
+          auto ld = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (PAIR) ptx::tma_load_2d_pair(dst, m, &full_bar[stage], c0, c1);
+            else ptx::tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+          };
           if (!Cfg::TW) {
-            ptx::tma_load_2d(sw, &S.tmW, &full_bar[stage], S.w_c0 + k0, S.w_c1 + ti.c0);
+            ld(sw, &S.tmW, S.w_c0 + k0, S.w_c1 + ti.c0);
           } else {
 #pragma unroll
-            for (int i = 0; i < UMMA_BC / 64; ++i)
-              ptx::tma_load_2d(sw + i * 8192, &S.tmW, &full_bar[stage], S.w_c0 + ti.c0 + 64 * i, S.w_c1 + k0);
+            for (int i = 0; i < UMMA_BC / 64; ++i) ld(sw + i * 8192, &S.tmW, S.w_c0 + ti.c0 + 64 * i, S.w_c1 + k0);
           }
           if (!Cfg::TX) {
-            ptx::tma_load_2d(sx, &S.tmX, &full_bar[stage], S.x_c0 + k0, S.x_c1 + ti.r0);
+            ld(sx, &S.tmX, S.x_c0 + k0, S.x_c1 + xr0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BR / 64; ++i)
-              ptx::tma_load_2d(sx + i * 8192, &S.tmX, &full_bar[stage], S.x_c0 + ti.r0 + 64 * i, S.x_c1 + k0);
+            for (int i = 0; i < Cfg::XR / 64; ++i) ld(sx + i * 8192, &S.tmX, S.x_c0 + xr0 + 64 * i, S.x_c1 + k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(UMMA_BC, BR, Cfg::TW ? 1 : 0, Cfg::TX ? 1 : 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t smem_u = ptx::smem_u32(smem);
-    const uint64_t dw_base = Cfg::TW ? ptx::make_smem_desc(smem_u, 8192, 1024) : ptx::make_smem_desc(smem_u, 16, 1024);
-    const uint64_t dx_base = Cfg::TX ? ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 8192, 1024)
-                                     : ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 16, 1024);
-    constexpr uint32_t W_KK = (Cfg::TW ? 2048 : 32) >> 4, X_KK = (Cfg::TX ? 2048 : 32) >> 4;
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const Tile ti = decode(t);
-      const int b = it & 1, n = it >> 1;
-      ptx::mbar_wait(&tmem_empty[b], (n & 1) ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t dcol = tmem_base + (uint32_t)(b * BR);
-      const int nchunks = ti.kc_end - ti.kc_begin;
-      for (int kc = 0; kc < nchunks; ++kc) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (whole warp loops, one elected lane issues; leader CTA of a pair) ==========
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * UMMA_BC : UMMA_BC, BR, Cfg::TW ? 1 : 0, Cfg::TX ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t smem_u = ptx::smem_u32(smem);
+      const uint64_t dw_base = Cfg::TW ? ptx::make_smem_desc(smem_u, 8192, 1024) : ptx::make_smem_desc(smem_u, 16, 1024);
+      const uint64_t dx_base = Cfg::TX ? ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 8192, 1024)
+                                       : ptx::make_smem_desc(smem_u + Cfg::W_BYTES, 16, 1024);
+      constexpr uint32_t W_KK = (Cfg::TW ? 2048 : 32) >> 4, X_KK = (Cfg::TX ? 2048 : 32) >> 4;
+      int it = 0;
+      for (int t = worker; t < ntiles; t += nworkers, ++it) {
+        const Tile ti = decode(t);
+        const int b = it & 1, n = it >> 1;
+        ptx::mbar_wait(&tmem_empty[b], (n & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint64_t so = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
-        if (ptx::elect_one()) {
+        const uint32_t dcol = tmem_base + (uint32_t)(b * BR);
+        const int nchunks = ti.kc_end - ti.kc_begin;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t so = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < UMMA_BK / 16; ++kk)
-            ptx::umma_bf16(dcol, dw_base + so + (uint64_t)(kk * W_KK), dx_base + so + (uint64_t)(kk * X_KK), idesc,
-                           (kc > 0 || kk > 0) ? 1u : 0u);
-          ptx::umma_commit(&empty_bar[stage]);
+            for (int kk = 0; kk < UMMA_BK / 16; ++kk) {
+              const uint64_t dw = dw_base + so + (uint64_t)(kk * W_KK), dx = dx_base + so + (uint64_t)(kk * X_KK);
+              if (PAIR) ptx::umma_bf16_pair(dcol, dw, dx, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+              else ptx::umma_bf16(dcol, dw, dx, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            }
+            if (PAIR) ptx::umma_commit_pair(&empty_bar[stage]);
+            else ptx::umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (ptx::elect_one()) {
+          if (nchunks > 0) {
+            if (PAIR) ptx::umma_commit_pair(&tmem_full[b]);
+            else ptx::umma_commit(&tmem_full[b]);
+          } else {
+            ptx::mbar_arrive(&tmem_full[b]);
+            if (PAIR) ptx::mbar_arrive_remote(&tmem_full[b], 1);
+          }
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (ptx::elect_one()) {
-        if (nchunks > 0) ptx::umma_commit(&tmem_full[b]);
-        else ptx::mbar_arrive(&tmem_full[b]);
-      }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int t = worker; t < ntiles; t += nworkers, ++it) {
       const Tile ti = decode(t);
       const UmmaProblem<Epi>& P = batch.p[ti.prob];
       const int b = it & 1, n = it >> 1;
       const int col = ti.c0 + q * 32 + lane;
-      const bool col_ok = col < P.N && ti.r0 < P.M;
+      const bool tile_ok = ti.c0 < P.N && ti.r0 < P.M;
+      const bool col_ok = col < P.N && tile_ok;
       typename Epi::Col cc;
       if (col_ok) Epi::col_init(P.epi, col, cc);
       const int nchunks = ti.kc_end - ti.kc_begin;
       ptx::mbar_wait(&tmem_full[b], n & 1);
       ptx::tc_fence_after();
-      if (ti.c0 < P.N && ti.r0 < P.M) {
+      if (tile_ok) {
 #pragma unroll 1
         for (int c = part; c < BR / 16; c += Cfg::PARTS) {
           const int row0 = ti.r0 + c * 16;
@@ -553,14 +582,19 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[b]);
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&tmem_empty[b]);
+        else ptx::mbar_arrive_remote(&tmem_empty[b], 0);
+      }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) ptx::tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

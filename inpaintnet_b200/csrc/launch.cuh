@@ -104,11 +104,25 @@ int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int ma
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int ntx = cdiv(maxN, UMMA_BC), nty = cdiv(maxM, Cfg::BR);
+  const int ntx = cdiv(maxN, Cfg::PAIR ? 2 * UMMA_BC : UMMA_BC), nty = cdiv(maxM, Cfg::BR);
   const long long ntiles = (long long)ntx * nty * nprob * batch.split_k;
   IPN_REQUIRE(ntiles < (1LL << 30), IPN_ERR_ARG, "too many tiles");
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(batch, ntx, nty, (int)ntiles);
+  const int per = Cfg::PAIR ? 2 : 1;
+  const long long workers = ntiles < sms / per ? ntiles : sms / per;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(workers * per), 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = per;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, batch, ntx, nty, (int)ntiles));
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }
