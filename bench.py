@@ -197,8 +197,16 @@ def run_inpaint(args, world, rank, timed):
         query(i)
     reps = 5
     ms = timed(query, reps)
+    kern = None
+    if rank == 0:   # per-kernel-class breakdown of one query batch
+        from inpaintnet_b200 import ops
+        ops.prof_enable(True)
+        query(0)
+        kern = {n: {"launches": k["launches"], "ms": round(k["ms"], 4)} for n, k in
+                sorted(ops.prof_report().items(), key=lambda kv: -kv[1]["ms"])}
+        ops.prof_enable(False)
     return {"metric": "inpaint_queries_per_sec", "value": world * Q * reps / (ms / 1e3), "unit": "queries/s",
-            "queries_per_gpu": Q, "split": "6/4/6", "ms_per_batch": ms / reps, "end_to_end": True,
+            "queries_per_gpu": Q, "split": "6/4/6", "ms_per_batch": ms / reps, "end_to_end": True, "kernels": kern,
             "note": "host int32 tokens -> H2D -> encode 12 context measures + LatentRNN + argmax decode of 4 gap "
                     "measures -> D2H tokens; target-encode (unused by the non-autoregressive model) skipped"}
 

@@ -126,6 +126,24 @@ typedef struct {
 } IpnGemm;
 int ipn_gemm(const IpnGemm* g, void* stream);
 
+/* Hoisted all-timestep GRU input projection written directly in the layout the persistent layer kernel
+ * reads (so no relayout pass is needed): out = blocked bf16 [rows, 3, H] of
+ *   r, z: 0.5 * (X W_ih^T + b_ih + b_hh)      n: X W_ih^T + b_ih
+ * Pass the result as IpnGruDir.P with P_blocked = 1.  rows % 128 == 0; tcgen05 core (bf16 operands) only. */
+typedef struct {
+  const void* X; /* [rows, K] bf16, row stride ldx */
+  long long ldx;
+  long long rows;
+  int K;
+  const void* w_ih; /* [3H, K] bf16, row stride ldw */
+  long long ldw;
+  const float* b_ih;
+  const float* b_hh;
+  int H;
+  void* out;
+} IpnGruInproj;
+int ipn_gru_inproj_blocked(const IpnGruInproj* p, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * GRU layer (all directions of ONE layer), forward.  replaces torch.nn.GRU.forward:
  * MeasureVAE/encoder.py:125; MeasureVAE/decoder.py:470,498; LatentRNN/latent_rnn.py:188,190,
@@ -163,6 +181,7 @@ typedef struct {
   void* final_out_dir; /* when non-null: this direction writes its final state here instead of IpnGruLayer.final_out */
   int final_dir_dt;
   long long ld_final_dir;
+  int P_blocked; /* P was produced by ipn_gru_inproj_blocked (persistent kernel only; table/pvec must be null) */
 } IpnGruDir;
 
 typedef struct {

@@ -34,7 +34,13 @@ class Gemm(C.Structure):
 class GruDir(C.Structure):
     _fields_ = [("w_hh", vp), ("b_hh", vp), ("P", vp), ("ldP", ll), ("P_bcast", i32), ("table", vp),
                 ("ld_table", ll), ("tok", vp), ("pvec", vp), ("hseq", vp), ("gates", vp), ("reverse", i32),
-                ("y_col0", i32), ("final_col0", i32), ("final_out_dir", vp), ("final_dir_dt", i32), ("ld_final_dir", ll)]
+                ("y_col0", i32), ("final_col0", i32), ("final_out_dir", vp), ("final_dir_dt", i32), ("ld_final_dir", ll),
+                ("P_blocked", i32)]
+
+
+class GruInproj(C.Structure):
+    _fields_ = [("X", vp), ("ldx", ll), ("rows", ll), ("K", i32), ("w_ih", vp), ("ldw", ll), ("b_ih", vp), ("b_hh", vp),
+                ("H", i32), ("out", vp)]
 
 
 class GruLayer(C.Structure):
@@ -86,7 +92,7 @@ class TickDecode(C.Structure):
                 ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap), ("gates_blocked", i32)]
 
 
-STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
+STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruInproj, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
                     PackItem, TickDecode]
 
 # name -> (restype, argtypes); every symbol declared in include/inpaintnet_b200.h
@@ -100,6 +106,7 @@ SYMBOLS = {
     "ipn_dbg_set_timing_buffer": (None, [vp]),
     "ipn_prof_report": (i32, [C.c_char_p, i32]),
     "ipn_gemm": (i32, [C.POINTER(Gemm), vp]),
+    "ipn_gru_inproj_blocked": (i32, [C.POINTER(GruInproj), vp]),
     "ipn_gru_layer_fwd": (i32, [C.POINTER(GruLayer), vp]),
     "ipn_gru_layer_bwd": (i32, [C.POINTER(GruLayerBwd), vp]),
     "ipn_gru_layer_fwd_ws_bytes": (ll, [C.POINTER(GruLayer)]),

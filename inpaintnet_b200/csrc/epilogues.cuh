@@ -133,6 +133,48 @@ struct EpiLinear {
 };
 
 // =============================================================================================
+// Blocked GRU input projection (persistent GEMM with the operand roles swapped: TMEM lanes = activation
+// rows R, accumulator columns = gate units n in [0, 3H)): one call = 8 consecutive units of one row = one
+// 16-byte vector of the blocked layout vec16(R, g, u) = ((R/128*3 + g)*(H/8) + u/8)*128 + R%128 that the
+// persistent GRU layer kernel reads (gru_persist.cuh).  Folds b_ih, the r/z part of b_hh and the 0.5 of
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5, exactly like gru_prep_p_kernel.
+// =============================================================================================
+struct EpiBlockedP {
+  template <class PP>
+  static __device__ __forceinline__ unsigned long long* dbg_buf(const PP&) { return nullptr; }
+  static constexpr int G = 1;
+  static constexpr int NARR = 0;
+  struct Params {
+    uint4* out;
+    const float* b_ih;
+    const float* b_hh;
+    int H;
+  };
+  struct Col {};
+  static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
+  template <int W>
+  static __device__ __forceinline__ void applyT(const Params& p, const Col&, int col, int row0, int nv, float (&acc)[1][W]) {
+    static_assert(W == 8, "one 16-byte vector per call");
+    const int H = p.H;
+    const int g = row0 / H, u = row0 - g * H;
+    const float4 b0 = *reinterpret_cast<const float4*>(p.b_ih + row0), b1 = *reinterpret_cast<const float4*>(p.b_ih + row0 + 4);
+    float f[8] = {acc[0][0] + b0.x, acc[0][1] + b0.y, acc[0][2] + b0.z, acc[0][3] + b0.w,
+                  acc[0][4] + b1.x, acc[0][5] + b1.y, acc[0][6] + b1.z, acc[0][7] + b1.w};
+    if (g < 2) {
+      const float4 c0 = *reinterpret_cast<const float4*>(p.b_hh + row0), c1 = *reinterpret_cast<const float4*>(p.b_hh + row0 + 4);
+      f[0] = 0.5f * (f[0] + c0.x); f[1] = 0.5f * (f[1] + c0.y); f[2] = 0.5f * (f[2] + c0.z); f[3] = 0.5f * (f[3] + c0.w);
+      f[4] = 0.5f * (f[4] + c1.x); f[5] = 0.5f * (f[5] + c1.y); f[6] = 0.5f * (f[6] + c1.z); f[7] = 0.5f * (f[7] + c1.w);
+    }
+    uint4 o;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    const long long R = col;
+    p.out[(((R >> 7) * 3 + g) * (H >> 3) + (u >> 3)) * 128 + (R & 127)] = o;
+  }
+};
+
+// =============================================================================================
 // GRU forward step:  acc[g] = (h_prev W_hh^T)[row, g*H + col]   g in {r, z, n}
 // =============================================================================================
 struct GruFwdParams {

@@ -132,3 +132,33 @@ extern "C" int ipn_gemm(const IpnGemm* g, void* stream_) {
   ipn::set_error("ipn_gemm: layout transA=1,transB=0 is not provided by the tcgen05 core");
   return IPN_ERR_ARG;
 }
+
+// Blocked GRU input projection: see EpiBlockedP (epilogues.cuh) and include/inpaintnet_b200.h
+extern "C" int ipn_gru_inproj_blocked(const IpnGruInproj* q, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(q != nullptr && q->X && q->w_ih && q->b_ih && q->b_hh && q->out, IPN_ERR_ARG, "gru_inproj_blocked: null pointer");
+  IPN_PROPAGATE(ensure_device());
+  IPN_REQUIRE(q->rows > 0 && q->rows % 128 == 0 && q->H % 8 == 0 && q->H > 0 && q->K > 0, IPN_ERR_ARG,
+              "gru_inproj_blocked: rows must be a multiple of 128 and H of 8 (rows=%lld H=%d)", q->rows, q->H);
+  IPN_REQUIRE(q->rows < (1LL << 31), IPN_ERR_ARG, "gru_inproj_blocked: too many rows");
+  constexpr int BR = 256;
+  const int N3 = 3 * q->H;
+  const bool pair = (q->rows / 128) % 2 == 0;
+  UmmaBatch<EpiBlockedP> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  UmmaProblem<EpiBlockedP>& P = b.p[0];
+  P.nseg = 1;
+  P.M = N3;                 // "rows" of the tile = gate units (X side, MMA N)
+  P.N = (int)q->rows;       // "columns" = activation rows (W side, TMEM lanes)
+  P.gate_stride = 0;
+  HostOperand x{q->w_ih, q->ldw, 0, N3, 0, 0};
+  HostOperand w{q->X, q->ldx, 0, q->rows, 0, 0};
+  IPN_PROPAGATE(fill_umma_seg(P.seg[0], x, w, q->K, pair ? BR / 2 : BR));
+  P.epi.out = reinterpret_cast<uint4*>(q->out);
+  P.epi.b_ih = q->b_ih;
+  P.epi.b_hh = q->b_hh;
+  P.epi.H = q->H;
+  if (pair) return launch_umma_persist<UmmaPCfg<BR, false, false, true>, EpiBlockedP>(b, 1, N3, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
+  return launch_umma_persist<UmmaPCfg<BR, false, false, false>, EpiBlockedP>(b, 1, N3, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
+}

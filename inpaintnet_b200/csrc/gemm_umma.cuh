@@ -386,7 +386,7 @@ struct UmmaPCfg {
 // ntx counts column tiles of 128 (PAIR: column-tile PAIRS of 256); grid.x CTAs (PAIR: clusters of 2)
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, int nty, int ntiles) {
+umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, int nty, int ntiles, int row_fastest) {
   static_assert(Epi::G == 1, "the persistent GEMM serves single-accumulator epilogues");
   constexpr int BR = Cfg::BR, STAGES = Cfg::STAGES;
   constexpr bool PAIR = Cfg::PAIR;
@@ -435,8 +435,11 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
   struct Tile { int prob, c0, r0, kc_begin, kc_end, chunks_seg0; };
   auto decode = [&](int t) {
     Tile o;
-    const int tx = t % ntx, rest = t / ntx;   // column tile fastest: concurrent CTAs share the X row tile, W stays in L2
-    const int ty = rest % nty, z = rest / nty;
+    // column tile fastest (default): concurrent CTAs share the X row tile, W stays in L2; row tile fastest when
+    // the streamed (large) operand sits on the W side (roles swapped, EpiBlockedP)
+    int tx, ty, z;
+    if (row_fastest) { ty = t % nty; const int rest = t / nty; tx = rest % ntx; z = rest / ntx; }
+    else { tx = t % ntx; const int rest = t / ntx; ty = rest % nty; z = rest / nty; }
     o.prob = z / batch.split_k;
     const int ksplit = z - o.prob * batch.split_k;
     const UmmaProblem<Epi>& P = batch.p[o.prob];

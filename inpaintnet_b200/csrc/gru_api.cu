@@ -36,6 +36,7 @@ static int check_layer_common(int core, int act_dt, int T, int B_total, int H, i
 }
 
 // gru_persist.cu / gru_persist_bwd.cu
+bool persist_enabled();
 bool gru_persist_fwd_shape_ok(const IpnGruLayer* L);
 long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L);
 int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStream_t stream);
@@ -60,7 +61,7 @@ extern "C" int ipn_gru_persist_eligible(int core, int act_dt, int B_total, int H
   IpnGruLayerBwd L;
   memset(&L, 0, sizeof(L));
   L.core = core; L.act_dt = act_dt; L.T = 1; L.B_total = B_total; L.H = H; L.row0 = 0; L.nrows = B_total; L.ndir = 0;
-  return gru_persist_bwd_shape_ok(&L) ? 1 : 0;
+  return (persist_enabled() && gru_persist_bwd_shape_ok(&L)) ? 1 : 0;
 }
 
 namespace ipn { unsigned long long* g_dbg_timing = nullptr; }
@@ -81,6 +82,8 @@ extern "C" int ipn_gru_layer_fwd(const IpnGruLayer* L, void* stream_) {
     IPN_REQUIRE(!D.table || D.tok, IPN_ERR_ARG, "gru_layer_fwd: table without tokens");
   }
   if (L->ws != nullptr && gru_persist_fwd_shape_ok(L)) return gru_persist_fwd(L, L->ws, L->ws_bytes, stream);
+  for (int d = 0; d < L->ndir; ++d)
+    IPN_REQUIRE(!L->dir[d].P_blocked, IPN_ERR_ARG, "gru_layer_fwd: P_blocked needs the persistent kernel (workspace + eligible shape)");
   IPN_REQUIRE(!L->gates_blocked || (L->core == IPN_CORE_UMMA && Bt % 128 == 0 && H % 8 == 0), IPN_ERR_ARG,
               "gru_layer_fwd: gates_blocked needs the tcgen05 core and B_total %% 128 == 0");
 

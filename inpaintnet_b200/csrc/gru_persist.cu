@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static bool persist_enabled() {
+bool persist_enabled() {
   static const int on = getenv("IPN_PERSIST") ? atoi(getenv("IPN_PERSIST")) : 1;
   return on != 0;
 }
@@ -433,6 +433,7 @@ bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
     if (D.y_col0 % 8 != 0) return false;
     if (D.P != nullptr && (D.ldP % 8 != 0 || !al16(D.P))) return false;
     if (D.table != nullptr && (D.ld_table % 4 != 0 || !al16(D.table))) return false;
+    if (D.P_blocked && (D.P == nullptr || D.table != nullptr || D.pvec != nullptr || D.P_bcast)) return false;
     if (D.gates != nullptr && !al16(D.gates)) return false;
   }
   return true;
@@ -474,7 +475,9 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     o.y_col0 = D.y_col0;
     o.gates = reinterpret_cast<uint4*>(D.gates);
     save = save || D.gates != nullptr;
-    {
+    if (D.P_blocked) {
+      o.Pblk = reinterpret_cast<const uint4*>(D.P);
+    } else {
       o.Pblk = reinterpret_cast<const uint4*>(wsp);
       PrepP q;
       q.P = reinterpret_cast<const __nv_bfloat16*>(D.P);

@@ -92,7 +92,7 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
 
 template <class Cfg, class Epi>
 int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
-                        const char* tag = "umma") {
+                        const char* tag = "umma", int row_fastest = 0) {
   ProfScope prof(tag, batch_flops(batch.p, nprob, Epi::G), 0.0, stream);
   static bool configured = false;
   static int sms = 148;
@@ -122,7 +122,7 @@ int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int ma
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, batch, ntx, nty, (int)ntiles));
+  IPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, batch, ntx, nty, (int)ntiles, row_fastest));
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }

@@ -92,9 +92,17 @@ def _workspace(nbytes):
     return torch.empty(nbytes, dtype=torch.uint8, device="cuda")
 
 
+def gru_inproj_blocked(X, ldx, rows, K, w_ih, ldw, b_ih, b_hh, H, out):
+    """out (blocked bf16 [rows,3,H]) = folded input projection of a GRU layer direction; see ipn_gru_inproj_blocked"""
+    q = L.GruInproj()
+    q.X, q.ldx, q.rows, q.K, q.w_ih, q.ldw, q.b_ih, q.b_hh, q.H, q.out = X, ldx, rows, K, w_ih, ldw, b_ih, b_hh, H, out
+    L.check(lib().ipn_gru_inproj_blocked(C.byref(q), stream()))
+
+
 def gru_dir(w_hh, b_hh, hseq, gates=0, P=0, ldP=0, P_bcast=0, table=0, ld_table=0, tok=0, pvec=0, reverse=0,
-            y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0):
+            y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0, P_blocked=0):
     d = L.GruDir()
+    d.P_blocked = P_blocked
     d.final_out_dir, d.final_dir_dt, d.ld_final_dir = final_out or None, final_dt, ld_final
     d.w_hh, d.b_hh, d.P, d.ldP, d.P_bcast = w_hh, b_hh, P or None, ldP, P_bcast
     d.table, d.ld_table, d.tok, d.pvec = table or None, ld_table, tok or None, pvec or None
