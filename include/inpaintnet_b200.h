@@ -368,8 +368,11 @@ typedef struct {
   IpnRowMap wmap;     /* else: weights + wmap(b) + t*V   and   samples + smap(b) + t */
   IpnRowMap smap;
   int gates_blocked;  /* see IpnGruLayer.gates_blocked */
+  void* ws;           /* nullable: ipn_tick_decode_ws_bytes() bytes; with it (and an eligible shape) every tick's two  */
+  long long ws_bytes; /* GRU steps run the persistent layer kernel on the tick's row window instead of the per-step one */
 } IpnTickDecode;
 int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream);
+long long ipn_tick_decode_ws_bytes(const IpnTickDecode* p);
 
 /* ------------------------------------------------------------------------------------------
  * random numbers (Philox4x32-10, counter = element index): dropout keep-masks and N(0,1) noise.

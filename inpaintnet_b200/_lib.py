@@ -89,7 +89,7 @@ class TickDecode(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("B", i32), ("H", i32), ("V", i32), ("l0", GruDir), ("l1", GruDir),
                 ("yt0", vp), ("yt1", vp), ("mask", vp), ("mask_scale", f32), ("w_ih1", vp), ("b_ih1", vp),
                 ("Pt1", vp), ("w_v", vp), ("b_v", vp), ("weights", vp), ("samples", vp), ("tokprev", vp),
-                ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap), ("gates_blocked", i32)]
+                ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap), ("gates_blocked", i32), ("ws", vp), ("ws_bytes", ll)]
 
 
 STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruInproj, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
@@ -126,6 +126,7 @@ SYMBOLS = {
     "ipn_dlogits_relayout": (i32, [vp, vp, i32, i32, vp, i32, ll, vp]),
     "ipn_dlogits_relayout_mapped": (i32, [vp, vp, i32, i32, C.POINTER(RowMap), vp, i32, ll, vp]),
     "ipn_tick_decode_argmax": (i32, [C.POINTER(TickDecode), vp]),
+    "ipn_tick_decode_ws_bytes": (ll, [C.POINTER(TickDecode)]),
     "ipn_rng_keep_mask": (i32, [C.c_ulonglong, C.c_ulonglong, ll, f32, vp, vp]),
     "ipn_rng_normal": (i32, [C.c_ulonglong, C.c_ulonglong, ll, vp, vp]),
     "ipn_reparam_fwd": (i32, [vp, vp, vp, ll, vp, vp, i32, vp]),

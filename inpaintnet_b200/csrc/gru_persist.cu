@@ -22,11 +22,14 @@ struct PrepP {
   const float* b_hh;
   uint4* out;
   int H, Bt;
+  int ntw, tt_min, row0;   // window: blockIdx.x = (tt - tt_min) * ntw + tile ; rows tt*Bt + row0 + tile*128 ...
 };
 
 __global__ void __launch_bounds__(256) gru_prep_p_kernel(PrepP p) {
   __shared__ uint4 tile[128 * 8];
-  const int rt = blockIdx.x, g = blockIdx.y, c = blockIdx.z;
+  const int g = blockIdx.y, c = blockIdx.z;
+  const int lt = blockIdx.x;                               // local tile index (also the output tile index)
+  const long long Rbase = (long long)(p.tt_min + lt / p.ntw) * p.Bt + p.row0 + (lt % p.ntw) * 128;
   const int H = p.H;
   const int i = threadIdx.x;
   const int vec = i & 7;
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) gru_prep_p_kernel(PrepP p) {
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     const int row = pass * 32 + (i >> 3);
-    const long long R = (long long)rt * 128 + row;
+    const long long R = Rbase + row;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = 0.f;
@@ -65,18 +68,20 @@ __global__ void __launch_bounds__(256) gru_prep_p_kernel(PrepP p) {
   for (int pass = 0; pass < 4; ++pass) {
     const int v = pass * 2 + (i >> 7), row = i & 127;
     const uint4 u = tile[row * 8 + (v ^ (row & 7))];
-    p.out[(((long long)rt * 3 + g) * (H / 8) + c * 8 + v) * 128 + row] = u;
+    p.out[(((long long)lt * 3 + g) * (H / 8) + c * 8 + v) * 128 + row] = u;
   }
 }
 
 // y[R, col0 + u] = keep[R, col0 + u] ? y * scale : 0   (inter-layer dropout applied after the layer kernel)
 __global__ void gru_mask_y_kernel(__nv_bfloat16* y, long long ld_y, const unsigned char* mask, long long ld_mask,
-                                  int col0, int H, long long rows, float scale) {
+                                  int col0, int H, long long rows, float scale, int nrows, int Bt, int tt_min, int row0) {
+  // rows = NS * nrows window rows: local row l -> time tt_min + l / nrows, batch row row0 + l % nrows
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vpr = H / 8;
   if (idx >= rows * vpr) return;
-  const long long R = idx / vpr;
-  const int u = (int)(idx - R * vpr) * 8;
+  const long long l = idx / vpr;
+  const long long R = (long long)(tt_min + l / nrows) * Bt + row0 + l % nrows;
+  const int u = (int)(idx - l * vpr) * 8;
   uint4* yp = reinterpret_cast<uint4*>(y + R * ld_y + col0 + u);
   const uint2 m = *reinterpret_cast<const uint2*>(mask + R * ld_mask + col0 + u);
   float f[8];
@@ -109,8 +114,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   constexpr int UPC = PAIR ? 32 : 64;                              // hidden units of a chunk staged by this CTA
   const GruPersistFwdDir& D = p.d[blockIdx.y];
   const int H = p.H, KB = H >> 6, T = p.T;
+  const int NS = p.s_end - p.s_begin;   // processing steps s_begin .. s_end-1 (loop index t = s - s_begin)
   const int Bt = p.Bt;
-  const int rbase = blockIdx.x * GP_ROWS;
+  const int rbase = p.row0 + blockIdx.x * GP_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
@@ -167,16 +173,16 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       uint32_t phase = 0;
       // the epilogue's input-projection tiles are pulled from HBM into L2 well ahead of their use
       auto prefetch_p = [&](int t, int c) {
-        if (t >= T || (p.dbg & 16)) return;
-        const int tt = D.reverse ? T - 1 - t : t;
-        const long long rt = ((long long)tt * Bt + rbase) >> 7;
+        if (t >= NS || (p.dbg & 16)) return;
+        const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
+        const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
         const int vpr = H >> 3;
 #pragma unroll
         for (int g = 0; g < 3; ++g)
           ptx::bulk_prefetch_l2(D.Pblk + ((rt * 3 + g) * vpr + c * 8) * 128, 8 * 128 * 16);
       };
       prefetch_p(0, 0);
-      for (int t = 0; t < T; ++t)
+      for (int t = 0; t < NS; ++t)
         for (int c = 0; c < KB; ++c)
           for (int kb = 0; kb < KB; ++kb) {
             if (kb == 0) prefetch_p(c + 1 == KB ? t + 1 : t, c + 1 == KB ? 0 : c + 1);
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       const long long t_begin = clock64();
       const uint64_t descA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024);
       const uint64_t descW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024);
-      for (int t = 0; t < T; ++t)
+      for (int t = 0; t < NS; ++t)
         for (int c = 0; c < KB; ++c, ++i) {
           const int b = i & 1, n = i >> 1;
           wait_acc(&tmem_empty[b], (n & 1) ^ 1, tm, w_te);
@@ -254,8 +260,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       int i = 0;
       const bool tm = p.timing != nullptr;
       long long w_sr = 0, w_st = 0;
-      for (int t = 0; t < T; ++t) {
-        const int tt = D.reverse ? T - 1 - t : t;
+      for (int t = 0; t < NS; ++t) {
+        const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
         const int out_slot = D.reverse ? tt : tt + 1;
         for (int c = 0; c < KB; ++c, ++i) {
           wait_acc(stg_ready, i & 1, tm, w_sr);
@@ -280,8 +286,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     if (lane == 0) {
       const bool tm = p.timing != nullptr;
       long long w_fr = 0, w_hs = 0;
-      for (int t = 0; t < T; ++t) {
-        const int tt = D.reverse ? T - 1 - t : t;
+      for (int t = 0; t < NS; ++t) {
+        const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
         const int in_slot = D.reverse ? tt + 1 : tt;
         for (int kb = 0; kb < KB; ++kb) {
           if (t > 0) {
@@ -316,8 +322,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     const bool ldp = !(p.dbg & 1);
     // input projection, register double-buffered one chunk ahead (the tiles were prefetched into L2 earlier)
     auto load_p = [&](uint4 (&dst)[3][2], int t, int c) {
-      const int tt = D.reverse ? T - 1 - t : t;
-      const long long rt = ((long long)tt * Bt + rbase) >> 7;
+      const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
+      const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
       const uint4* base = D.Pblk + (rt * 3 * vpr + c * 8 + sub * 2) * 128 + row;
 #pragma unroll
       for (int g = 0; g < 3; ++g)
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     };
     // one chunk of the flattened (t, c) sequence
     auto do_chunk = [&](int t, int c, int i) {
-      const int tt = D.reverse ? T - 1 - t : t;
+      const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
       const long long rt = ((long long)tt * Bt + rbase) >> 7;  // 128-row tile index in time-ordered buffers
       const int b = i & 1, n = i >> 1;
       uint4 pv[3][2];
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     };
     {
       int i = 0, t = 0, c = 0;
-      const int total = T * KB;
+      const int total = NS * KB;
       while (i < total) {
         do_chunk(t, c, i);
         ++i; if (++c == KB) { c = 0; ++t; }
@@ -424,8 +430,9 @@ bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
   if (!persist_enabled()) return false;
   if (L->core != IPN_CORE_UMMA || L->act_dt != IPN_BF16) return false;
   if (L->H % 64 != 0 || L->H < 64 || L->H > 512) return false;
-  if (L->B_total % GP_ROWS != 0 || L->row0 != 0 || L->nrows != L->B_total) return false;
-  if (L->s_begin != 0 || L->s_end != L->T) return false;
+  if (L->B_total % GP_ROWS != 0 || L->row0 % GP_ROWS != 0 || L->nrows % GP_ROWS != 0 || L->nrows <= 0) return false;
+  if (L->row0 < 0 || L->row0 + L->nrows > L->B_total) return false;
+  if (L->s_begin < 0 || L->s_begin >= L->s_end || L->s_end > L->T) return false;
   if (L->y != nullptr && (L->ld_y % 8 != 0 || !al16(L->y))) return false;
   if (L->mask != nullptr && (L->ld_mask % 8 != 0 || reinterpret_cast<uintptr_t>(L->mask) % 8 != 0)) return false;
   for (int d = 0; d < L->ndir; ++d) {
@@ -441,7 +448,7 @@ bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
 
 long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L) {
   if (!gru_persist_fwd_shape_ok(L)) return 0;
-  long long per_dir = (long long)L->T * L->B_total * 3 * L->H * 2;
+  long long per_dir = (long long)(L->s_end - L->s_begin) * L->nrows * 3 * L->H * 2;
   return per_dir * L->ndir;
 }
 
@@ -452,12 +459,14 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   GruPersistFwd p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.H = H; p.Bt = Bt;
+  p.row0 = L->row0; p.s_begin = L->s_begin; p.s_end = L->s_end;
+  const int NS = L->s_end - L->s_begin, ntw = L->nrows / GP_ROWS;   // steps and row tiles of this call's window
   static const int dbg = getenv("IPN_GPF_DBG") ? atoi(getenv("IPN_GPF_DBG")) : 0;
   p.dbg = dbg;
   p.timing = g_dbg_timing;
-  const long long per_dir = (long long)T * Bt * 3 * H * 2;
+  const long long per_dir = (long long)NS * L->nrows * 3 * H * 2;
   static const int pair_on = getenv("IPN_GPF_PAIR") ? atoi(getenv("IPN_GPF_PAIR")) : 1;
-  const bool pair = pair_on && (Bt / GP_ROWS) % 2 == 0;
+  const bool pair = pair_on && ntw % 2 == 0;
   char* wsp = reinterpret_cast<char*>(ws);
   bool save = false;
   for (int d = 0; d < L->ndir; ++d) {
@@ -475,10 +484,15 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     o.y_col0 = D.y_col0;
     o.gates = reinterpret_cast<uint4*>(D.gates);
     save = save || D.gates != nullptr;
+    const int tt_min = D.reverse ? T - L->s_end : L->s_begin;   // earliest time index this call touches
     if (D.P_blocked) {
-      o.Pblk = reinterpret_cast<const uint4*>(D.P);
+      o.Pblk = reinterpret_cast<const uint4*>(D.P);   // global blocked layout over all T*Bt rows
+      o.p_t_stride = Bt / GP_ROWS;
+      o.p_t0 = L->row0 / GP_ROWS;
     } else {
-      o.Pblk = reinterpret_cast<const uint4*>(wsp);
+      o.Pblk = reinterpret_cast<const uint4*>(wsp);   // local layout: only this call's window
+      o.p_t_stride = ntw;
+      o.p_t0 = -(long long)tt_min * ntw;
       PrepP q;
       q.P = reinterpret_cast<const __nv_bfloat16*>(D.P);
       q.ldP = D.ldP; q.P_bcast = D.P_bcast;
@@ -486,7 +500,8 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
       q.pvec = D.pvec; q.b_hh = D.b_hh;
       q.out = reinterpret_cast<uint4*>(wsp);
       q.H = H; q.Bt = Bt;
-      dim3 grid((unsigned)((long long)T * Bt / 128), 3, H / 64);
+      q.ntw = ntw; q.tt_min = tt_min; q.row0 = L->row0;
+      dim3 grid((unsigned)((long long)NS * ntw), 3, H / 64);
       ProfScope prof("gru_prep_p", 0.0, (double)per_dir * (D.P != nullptr && !D.P_bcast ? 2.0 : 1.0), stream);
       gru_prep_p_kernel<<<grid, 256, 0, stream>>>(q);
       IPN_LAUNCH_CHECK();
@@ -502,12 +517,12 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
       *configured = true;
     }
     // algorithmic work of the whole layer: recurrent GEMM flops; bytes = P read + h write + saved gates + y
-    const double rows = (double)T * Bt * L->ndir;
+    const double rows = (double)NS * L->nrows * L->ndir;
     ProfScope prof("gru_layer_fwd_persist", 2.0 * rows * 3.0 * H * H,
                    rows * H * 2.0 * (3 + 1 + (save ? GP_GATE_ARRAYS : 0) + (L->y ? 1 : 0)), stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(Bt / GP_ROWS, L->ndir, 1);
+    cfg.gridDim = dim3(ntw, L->ndir, 1);
     cfg.blockDim = dim3(GP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -530,11 +545,13 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   // inter-layer dropout on the layer output
   if (L->y != nullptr && L->mask != nullptr) {
     for (int d = 0; d < L->ndir; ++d) {
-      const long long rows = (long long)T * Bt;
+      const long long rows = (long long)NS * L->nrows;
       const long long work = rows * (H / 8);
+      const int tt_min = L->dir[d].reverse ? T - L->s_end : L->s_begin;
       ProfScope prof("gru_mask_y", 0.0, (double)rows * H * 5.0, stream);
       gru_mask_y_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
-          reinterpret_cast<__nv_bfloat16*>(L->y), L->ld_y, L->mask, L->ld_mask, L->dir[d].y_col0, H, rows, L->mask_scale);
+          reinterpret_cast<__nv_bfloat16*>(L->y), L->ld_y, L->mask, L->ld_mask, L->dir[d].y_col0, H, rows, L->mask_scale,
+          L->nrows, Bt, tt_min, L->row0);
       IPN_LAUNCH_CHECK();
     }
   }
@@ -542,12 +559,13 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   for (int d = 0; d < L->ndir; ++d) {
     const IpnGruDir& D = L->dir[d];
     void* fo = D.final_out_dir != nullptr ? D.final_out_dir : L->final_out;
-    if (fo == nullptr) continue;
+    if (fo == nullptr || L->s_end != T) continue;   // the final state exists once the last step has run
     const int fdt = D.final_out_dir != nullptr ? D.final_dir_dt : L->final_dt;
     const long long ldf = D.final_out_dir != nullptr ? D.ld_final_dir : L->ld_final;
-    const char* src = reinterpret_cast<const char*>(D.hseq) + (long long)(D.reverse ? 0 : T) * Bt * H * 2;
-    char* dst = reinterpret_cast<char*>(fo) + (long long)D.final_col0 * (fdt == IPN_BF16 ? 2 : 4);
-    IPN_PROPAGATE(ipn_convert_2d(src, IPN_BF16, H, dst, fdt, ldf, Bt, H, stream));
+    const int fes = fdt == IPN_BF16 ? 2 : 4;
+    const char* src = reinterpret_cast<const char*>(D.hseq) + ((long long)(D.reverse ? 0 : T) * Bt + L->row0) * H * 2;
+    char* dst = reinterpret_cast<char*>(fo) + ((long long)L->row0 * ldf + D.final_col0) * fes;
+    IPN_PROPAGATE(ipn_convert_2d(src, IPN_BF16, H, dst, fdt, ldf, L->nrows, H, stream));
   }
   return IPN_OK;
 }

@@ -33,11 +33,14 @@ struct GruPersistFwdDir {
   uint4* gates;                 // blocked [T*Bt, 5, H], nullable
   const float* b_hh;
   const float* pvec;            // nullable
-  int reverse, y_col0, has_y, pad_;
+  int reverse, y_col0, has_y;
+  int p_t_stride;               // 128-row tile index of (time tt, tile x) in Pblk = tt * p_t_stride + p_t0 + x
+  long long p_t0;
 };
 struct GruPersistFwd {
   GruPersistFwdDir d[2];
   int T, H, Bt;
+  int row0, s_begin, s_end;   // window of this call: rows [row0, row0 + 128*gridDim.x), processing steps [s_begin, s_end)
   int dbg;                    // diagnostics (IPN_GPF_DBG): 1 no P loads, 2 no gate stores, 4 no gate math, 8 no W loads
   unsigned long long* timing; // per-CTA wait-cycle counters (ipn_dbg_set_timing_buffer), normally null
 };

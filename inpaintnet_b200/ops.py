@@ -184,6 +184,8 @@ def tick_decode_argmax(prec, B, H, V, l0, l1, yt0, yt1, mask, mask_scale, w_ih1,
     p.yt0, p.yt1, p.mask, p.mask_scale = yt0, yt1, mask or None, mask_scale
     p.w_ih1, p.b_ih1, p.Pt1, p.w_v, p.b_v = w_ih1, b_ih1, Pt1, w_v, b_v
     p.weights, p.samples, p.tokprev = weights, samples or None, tokprev
+    ws = _workspace(lib().ipn_tick_decode_ws_bytes(C.byref(p)))
+    p.ws, p.ws_bytes = (ws.data_ptr(), ws.numel()) if ws is not None else (None, 0)
     L.check(lib().ipn_tick_decode_argmax(C.byref(p), stream()))
 
 
