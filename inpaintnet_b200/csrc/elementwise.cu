@@ -316,7 +316,27 @@ __global__ void colsum_kernel(const void* X, int dt, long long ld, long long row
   if (c0 < cols) {
     const int nvalid = min(8, cols - c0);
     const bool vec = vec_ok(X, ld, dt) && nvalid == 8;
-    for (long long r = r0 + ry; r < r1; r += 16) {
+    long long r = r0 + ry;
+    if (vec && dt == IPN_BF16) {
+      // four independent 16-byte loads in flight per thread (the loop is otherwise latency bound)
+      const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(X);
+      for (; r + 48 < r1; r += 64) {
+        uint4 u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = *reinterpret_cast<const uint4*>(xb + (r + 16 * j) * ld + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h2[k]);
+            acc[2 * k] += f.x;
+            acc[2 * k + 1] += f.y;
+          }
+        }
+      }
+    }
+    for (; r < r1; r += 16) {
       float v[8];
       ld_act_n<8>(X, r * ld + c0, dt, vec, nvalid, v);
 #pragma unroll

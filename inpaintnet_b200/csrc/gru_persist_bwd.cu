@@ -265,19 +265,25 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       const int s = T - 1 - it;
       const int tt = D.reverse ? T - 1 - s : s;
       const long long rt = ((long long)tt * Bt + rbase) >> 7;
-      if (it > 0) {
-        ptx::mbar_wait(tmem_full, (it - 1) & 1);
-        ptx::tc_fence_after();
-      }
       for (int c = 0; c < KB; ++c, ++i) {
         const uint4* gp = D.gates + ((rt * GP_GATE_ARRAYS) * vpr + c * 8 + sub * 2) * 128 + row;
         const uint4* yp = D.dYblk != nullptr ? D.dYblk + (rt * vpr + c * 8 + sub * 2) * 128 + row : nullptr;
         const int u0 = c * 64 + sub * 16;
+        // all global loads of the chunk are issued up front (one memory round trip per chunk)
+        uint4 gv[2][5], yv[2];
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          const uint4 gr = ldg_stream(gp + v * 128), gz = ldg_stream(gp + astride + v * 128);
-          const uint4 gn = ldg_stream(gp + 2 * astride + v * 128), gh = ldg_stream(gp + 3 * astride + v * 128);
-          const uint4 gq = ldg_stream(gp + 4 * astride + v * 128);
+#pragma unroll
+          for (int a = 0; a < 5; ++a) gv[v][a] = ldg_stream(gp + a * astride + v * 128);
+          yv[v] = yp != nullptr ? ldg_stream(yp + v * 128) : make_uint4(0, 0, 0, 0);
+        }
+        if (c == 0 && it > 0) {   // the first chunk's loads are in flight while the GEMM phase finishes
+          ptx::mbar_wait(tmem_full, (it - 1) & 1);
+          ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const uint4 gr = gv[v][0], gz = gv[v][1], gn = gv[v][2], gh = gv[v][3], gq = gv[v][4];
           float dh[8];
           if (it > 0) ptx::tmem_ld8(tlane + (uint32_t)(u0 + v * 8), dh);
           else {
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           if (it > 0) ptx::tmem_ld_wait();
           if (yp != nullptr) {
             float dy[8];
-            unpack8(ldg_stream(yp + v * 128), dy);
+            unpack8(yv[v], dy);
 #pragma unroll
             for (int k = 0; k < 8; ++k) dh[k] += dy[k];
           }
