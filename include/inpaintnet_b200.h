@@ -123,6 +123,8 @@ typedef struct {
   float mul_scale;
   int accumulate;
   int split_k;
+  int max_ctas; /* 0 = one CTA per SM; >0 caps the persistent grid so that the GEMM can share the GPU with a kernel
+                   that holds the other SMs (weight-gradient GEMMs on a side stream under a persistent GRU layer kernel) */
 } IpnGemm;
 int ipn_gemm(const IpnGemm* g, void* stream);
 

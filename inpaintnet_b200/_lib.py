@@ -28,7 +28,7 @@ class Gemm(C.Structure):
                 ("out", vp), ("out_dt", i32), ("ld_out", ll), ("use_rowmap", i32), ("rowmap", RowMap),
                 ("split_cols", i32), ("split_stride", ll), ("bias", vp), ("act", i32), ("alpha", f32),
                 ("mul_src", vp), ("mul_dt", i32), ("ld_mul", ll), ("mul_mode", i32), ("mul_scale", f32),
-                ("accumulate", i32), ("split_k", i32)]
+                ("accumulate", i32), ("split_k", i32), ("max_ctas", i32)]
 
 
 class GruDir(C.Structure):

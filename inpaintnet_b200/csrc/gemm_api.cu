@@ -49,9 +49,9 @@ static int gemm_umma(const IpnGemm* g, int split_k, cudaStream_t stream) {
   const char* tag = TX ? "gemm_umma_tn_wgrad" : (TW ? "gemm_umma_nn_dgrad" : "gemm_umma_nt");
   if constexpr (BR >= 128) {
     if (pair)
-      return launch_umma_persist<UmmaPCfg<BR, TW, TX, true>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
+      return launch_umma_persist<UmmaPCfg<BR, TW, TX, true>, EpiLinear>(b, 1, g->M, g->N, stream, tag, 0, g->max_ctas);
   }
-  if (persist) return launch_umma_persist<UmmaPCfg<BR, TW, TX, false>, EpiLinear>(b, 1, g->M, g->N, stream, tag);
+  if (persist) return launch_umma_persist<UmmaPCfg<BR, TW, TX, false>, EpiLinear>(b, 1, g->M, g->N, stream, tag, 0, g->max_ctas);
   return launch_umma<Cfg, EpiLinear>(b, 1, g->M, g->N, stream, tag);
 }
 

@@ -92,7 +92,7 @@ int launch_umma(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cuda
 
 template <class Cfg, class Epi>
 int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int maxN, cudaStream_t stream,
-                        const char* tag = "umma", int row_fastest = 0) {
+                        const char* tag = "umma", int row_fastest = 0, int max_ctas = 0) {
   ProfScope prof(tag, batch_flops(batch.p, nprob, Epi::G), 0.0, stream);
   static bool configured = false;
   static int sms = 148;
@@ -108,7 +108,8 @@ int launch_umma_persist(const UmmaBatch<Epi>& batch, int nprob, int maxM, int ma
   const long long ntiles = (long long)ntx * nty * nprob * batch.split_k;
   IPN_REQUIRE(ntiles < (1LL << 30), IPN_ERR_ARG, "too many tiles");
   const int per = Cfg::PAIR ? 2 : 1;
-  const long long workers = ntiles < sms / per ? ntiles : sms / per;
+  const int ctas = (max_ctas > 0 && max_ctas < sms) ? (max_ctas < per ? per : max_ctas) : sms;
+  const long long workers = ntiles < ctas / per ? ntiles : ctas / per;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(workers * per), 1, 1);

@@ -119,6 +119,8 @@ class Trainer(ABC):
     def step(self):
         """Gradient all-reduce (sum over ranks, scaled by 1/world inside the Adam kernel) + fused Adam."""
         scale = 1.0
+        from .engine import SIDE
+        SIDE.join()   # weight-gradient GEMMs deferred to the side stream (normally already joined by the autograd callback)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             a = arena_of(self.model)
             allreduce_grads(a)
