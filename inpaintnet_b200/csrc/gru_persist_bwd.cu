@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) gru_prep_dy_kernel(PrepDY p) {
   }
 }
 
-constexpr int GPB_A_STAGES = 2;
-constexpr int GPB_W_RING = 96 * 1024;
+constexpr int GPB_A_STAGES = 3;        // A k-blocks are re-read from L2 (latency ~1.5 kcycles): 2 stages starve the MMAs
+constexpr int GPB_W_RING = 80 * 1024;
 constexpr int GPB_NBAR = 48;
 static inline int gpb_smem_bytes() { return GPB_A_STAGES * GP_KB_BYTES + GPB_W_RING + 4 * GP_KB_BYTES + GPB_NBAR * 8 + 16; }
 
@@ -79,14 +79,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 4 * GP_KB_BYTES);
   uint64_t* w_full = bars;             // [6]
   uint64_t* w_empty = bars + 6;        // [6]
-  uint64_t* a_full = bars + 12;        // [2]
-  uint64_t* a_empty = bars + 14;       // [2]
-  uint64_t* dg_stored = bars + 16;     // [8] chunk c of dP/dGn of this step is in global memory
-  uint64_t* tmem_full = bars + 24;     // GEMM phase complete: dh of the next step is in the accumulator
-  uint64_t* tmem_free = bars + 25;     // epilogue finished reading dh and writing the carry
-  uint64_t* stg_ready = bars + 26;
-  uint64_t* stg_free = bars + 27;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* a_full = bars + 12;        // [4]
+  uint64_t* a_empty = bars + 16;       // [4]
+  uint64_t* dg_stored = bars + 20;     // [8] chunk c of dP/dGn of this step is in global memory
+  uint64_t* tmem_full = bars + 28;     // GEMM phase complete: dh of the next step is in the accumulator
+  uint64_t* tmem_free = bars + 29;     // epilogue finished reading dh and writing the carry
+  uint64_t* stg_ready = bars + 30;
+  uint64_t* stg_free = bars + 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   if ((ptx::smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("inpaintnet_b200: gru_persist_bwd: shared memory base not 1024-byte aligned\n");
