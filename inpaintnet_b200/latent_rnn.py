@@ -15,9 +15,10 @@ from .ops import Precision
 
 class _LatentFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, past, future, arena, prec, model, n_gen, need_grad):
+    def forward(ctx, anchor, past, future, arena, prec, model, n_gen, need_grad, target, teacher_forcing):
         weights, samples, z_out, saved = engine_latent.latent_forward(arena, prec, model, past, future, n_gen,
-                                                                      model.training, need_grad)
+                                                                      model.training, need_grad, target=target,
+                                                                      teacher_forcing=teacher_forcing)
         ctx.state = (arena, prec, saved)
         ctx.mark_non_differentiable(samples)
         return weights, samples, z_out
@@ -29,7 +30,7 @@ class _LatentFn(torch.autograd.Function):
             raise RuntimeError("LatentRNN backward called twice or forward ran without grad")
         ctx.state = (arena, prec, None)
         engine_latent.latent_backward(arena, prec, saved, dweights, dz_out)
-        return (None,) * 8
+        return (None,) * 10
 
 
 class LatentRNN(Model):
@@ -99,18 +100,23 @@ class LatentRNN(Model):
         """past_context (batch, n_past, 24), future_context (batch, n_future, 24), target (batch, n_target, 24)
         -> weights (batch, measures_to_generate, 24, num_notes), samples (batch, 1, 24*measures_to_generate),
         gen_z (batch, measures_to_generate, z_dim)            -- latent_rnn.py:110-159.
-        The target-encode of latent_rnn.py:133 feeds nothing in the non-autoregressive model and is skipped."""
-        if self.auto_reg:
-            raise NotImplementedError(
-                "auto_reg=True (decode -> re-encode per measure, latent_rnn.py:241-260) is not on the B200 path yet; "
-                "the evaluation scripts use auto_reg=False (test_reconstruction.py:141)")
+        The target-encode of latent_rnn.py:133 only feeds the teacher-forced autoregressive model (its first
+        measures_to_generate - 1 measures); it is skipped everywhere else."""
+        if self.use_teacher_forcing and train:                       # latent_rnn.py:142-145
+            teacher_forcing = random.random() < self.teacher_forcing_prob
+        else:
+            teacher_forcing = False
         arena = arena_of(self)
         prec = Precision(self.precision or Fn.default_precision())
         anchor = _anchor(self)
         need_grad = torch.is_grad_enabled() and anchor is not None
         past = past_context if past_context.dtype == torch.int64 else past_context.long()
         fut = future_context if future_context.dtype == torch.int64 else future_context.long()
-        weights, samples, gen_z = _LatentFn.apply(anchor, past, fut, arena, prec, self, int(measures_to_generate), need_grad)
+        tgt = None
+        if self.auto_reg and teacher_forcing:
+            tgt = target if target.dtype == torch.int64 else target.long()
+        weights, samples, gen_z = _LatentFn.apply(anchor, past, fut, arena, prec, self, int(measures_to_generate), need_grad,
+                                                  tgt, teacher_forcing)
         return weights, samples, gen_z
 
     def save(self):

@@ -276,6 +276,54 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
     return torch.stack(ws, 1), torch.cat(ss, 2), z_out
 
 
+def latent_rnn_forward_autoreg(sd, past, future, target, n_gen, eps_past, eps_future, eps_target, eps_regen,
+                               teacher_forcing, num_layers=2):
+    """Autoregressive LatentRNN (auto_reg=True, the train_inpaintnet.py default; latent_rnn.py:142-153,219-261),
+    eval-mode dropout.  teacher_forcing=True: the generation GRU reads [z_past[-1], z_target[:-1]] in one call
+    (latent_rnn.py:148-149,230-240).  teacher_forcing=False: per gap measure one GRU call of length 1 with the
+    hidden state carried, linear, argmax decode, and the decoded tokens re-encoded by the frozen VAE
+    (rsample noise eps_regen[i] (B,Z)) as the next input (latent_rnn.py:246-260).
+    eps_target (B,n_t,Z) is the noise of the target encode.  Returns weights, samples, z_out as above."""
+    B = past.shape[0]
+    vp = "vae_model."
+
+    def z_seq(m, eps):                                                         # latent_rnn.py:161-174
+        n = m.shape[1]
+        mu, ls = encoder_forward(sd, m.reshape(-1, 24), 2, None, 0.0, prefix=vp + "encoder.")
+        return (mu + torch.exp(ls) * eps.reshape(-1, eps.shape[-1])).view(B, n, -1)
+
+    zp, zf = z_seq(past, eps_past), z_seq(future, eps_future)
+    Hc = sd["context_rnn_past.weight_hh_l0"].shape[1]
+    h0 = torch.zeros(num_layers * 2, B, Hc, dtype=zp.dtype)
+    _, hp = gru_forward(sd, "context_rnn_past.", zp, h0, num_layers, True)
+    _, hf = gru_forward(sd, "context_rnn_future.", zf, h0, num_layers, True)
+    hidden = torch.cat((hp, hf), 2)                                            # latent_rnn.py:140
+    lw, lb = sd["generation_linear.weight"], sd["generation_linear.bias"]
+    ws, ss = [], []
+    if teacher_forcing:
+        zt = z_seq(target, eps_target)
+        seed = torch.cat((zp[:, -1:], zt[:, :-1]), 1)                          # latent_rnn.py:149
+        out, _ = gru_forward(sd, "generation_rnn.", seed, hidden, num_layers, True)
+        z_out = linear(out.reshape(B * n_gen, -1), lw, lb).view(B, n_gen, -1)
+        for i in range(n_gen):
+            w, s = decoder_forward(sd, z_out[:, i], None, False, 2, prefix=vp + "decoder.")
+            ws.append(w)
+            ss.append(s)
+    else:
+        x = zp[:, -1:]                                                         # latent_rnn.py:151
+        zs = []
+        for i in range(n_gen):
+            out, hidden = gru_forward(sd, "generation_rnn.", x, hidden, num_layers, True)
+            gz = linear(out.reshape(B, -1), lw, lb)
+            zs.append(gz.unsqueeze(1))
+            w, s = decoder_forward(sd, gz, None, False, 2, prefix=vp + "decoder.")
+            ws.append(w)
+            ss.append(s)
+            x = z_seq(s, eps_regen[i])                                         # latent_rnn.py:259
+        z_out = torch.cat(zs, 1)
+    return torch.stack(ws, 1), torch.cat(ss, 2), z_out
+
+
 # --------------------------------------------------------------------------------------
 # LSTM + AnticipationRNN teacher-forced forward
 # (AnticipationRNN/anticipation_rnn_gauss_reg_model.py:14-39,348-404,437-532)

@@ -103,13 +103,16 @@ def adam_case():
     torch.save(dict(p0=p0, grads=grads, ps=ps), os.path.join(HERE, "adam.pt"))
 
 
-def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights):
+def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights, auto_reg=False, teacher_forcing=False):
+    """auto_reg=True: latent_rnn.py:142-153,219-261; teacher_forcing picks the branch (the coin is forced through
+    teacher_forcing_prob); eps_regen[i] is the rsample noise of the re-encode after gap measure i (no-TF branch)."""
     ds = FakeDataset(V)
     vae = R.MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
     vsd = recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), seed)
     vae.load_state_dict(vsd)
-    model = R.LatentRNN(ds, vae, 2, Hc, 0.5, torch.nn.GRU, auto_reg=False, teacher_forcing=False)
-    lsd = recipe.make_state_dict(recipe.latent_rnn_spec(Z, Hc), seed + 10)
+    model = R.LatentRNN(ds, vae, 2, Hc, 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg)
+    model.teacher_forcing_prob = 2.0 if teacher_forcing else -1.0
+    lsd = recipe.make_state_dict(recipe.latent_rnn_spec(Z, Hc, auto_reg=auto_reg), seed + 10)
     sd = dict(lsd)
     sd.update({"vae_model." + k: v for k, v in vsd.items()})
     model.load_state_dict(sd)
@@ -121,15 +124,17 @@ def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights)
     eps_p = recipe.make_normal((B, n_past, Z), seed + 2)
     eps_f = recipe.make_normal((B, n_fut, Z), seed + 3)
     eps_t = recipe.make_normal((B, n_tgt, Z), seed + 4)
+    eps_r = recipe.make_normal((n_tgt, B, Z), seed + 5)
     model.zero_grad()
-    with InjectedNoise([eps_p.reshape(-1, Z), eps_f.reshape(-1, Z), eps_t.reshape(-1, Z)]):
+    with InjectedNoise([eps_p.reshape(-1, Z), eps_f.reshape(-1, Z), eps_t.reshape(-1, Z)] + [eps_r[i] for i in range(n_tgt)]):
         weights, samples, gen_z = model(past, future, target, n_tgt, train=True)
     loss = R.LatentRNNTrainer.mean_crossentropy_loss_alt(weights=weights, targets=target)
     acc = R.LatentRNNTrainer.mean_accuracy_alt(weights=weights, targets=target)
     loss.backward()
     top2 = weights.detach().topk(2, dim=3).values
     fx = dict(V=V, H=H, Z=Z, Hc=Hc, B=B, seed=seed, past=past, future=future, target=target,
-              eps_past=eps_p, eps_future=eps_f, eps_target=eps_t,
+              eps_past=eps_p, eps_future=eps_f, eps_target=eps_t, eps_regen=eps_r, auto_reg=auto_reg,
+              teacher_forcing=teacher_forcing,
               weights=weights.detach().clone(), samples=samples.clone(), gen_z=gen_z.detach().clone(),
               loss=loss.item(), acc=acc.item(), margin=(top2[..., 0] - top2[..., 1]).clone(),
               grads=grads_summary(model, store_weights))
@@ -167,12 +172,24 @@ def arnn_case(name, V, B, seed):
 
 
 if __name__ == "__main__":
-    torch.manual_seed(0)
-    random.seed(0)
-    mvae_case("mvae_h32", V=20, H=32, Z=16, B=5, seed=100, store_weights=True, full_grads=True)
-    mvae_case("mvae_h64", V=47, H=64, Z=32, B=6, seed=200, store_weights=True, full_grads=True)
-    mvae_case("mvae_default", V=64, H=512, Z=256, B=4, seed=300, store_weights=False, full_grads=False)
-    adam_case()
-    latent_case("latent_h32", V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=2, n_fut=3, seed=400, store_weights=True)
-    latent_case("latent_default", V=64, H=512, Z=256, Hc=512, B=2, n_past=6, n_tgt=4, n_fut=6, seed=500, store_weights=False)
-    arnn_case("arnn_h32", V=20, B=2, seed=600)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""   # optional name prefix: regenerate just those fixtures
+    cases = [
+        ("mvae_h32", lambda n: mvae_case(n, V=20, H=32, Z=16, B=5, seed=100, store_weights=True, full_grads=True)),
+        ("mvae_h64", lambda n: mvae_case(n, V=47, H=64, Z=32, B=6, seed=200, store_weights=True, full_grads=True)),
+        ("mvae_default", lambda n: mvae_case(n, V=64, H=512, Z=256, B=4, seed=300, store_weights=False, full_grads=False)),
+        ("adam", lambda n: adam_case()),
+        ("latent_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=2, n_fut=3, seed=400,
+                                             store_weights=True)),
+        ("latent_default", lambda n: latent_case(n, V=64, H=512, Z=256, Hc=512, B=2, n_past=6, n_tgt=4, n_fut=6, seed=500,
+                                                 store_weights=False)),
+        ("arnn_h32", lambda n: arnn_case(n, V=20, B=2, seed=600)),
+        ("latent_ar_tf_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=3, n_fut=2, seed=700,
+                                                   store_weights=True, auto_reg=True, teacher_forcing=True)),
+        ("latent_ar_notf_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=2, n_tgt=3, n_fut=3, seed=828,
+                                                     store_weights=True, auto_reg=True, teacher_forcing=False)),
+    ]
+    for name, fn in cases:
+        if name.startswith(only):
+            torch.manual_seed(0)
+            random.seed(0)
+            fn(name)

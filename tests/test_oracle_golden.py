@@ -88,6 +88,24 @@ def test_latent_rnn_forward(name):
                 assert torch.allclose(mine, gg, atol=1e-6, rtol=2e-3), k
 
 
+@pytest.mark.parametrize("name", ["latent_ar_tf_h32", "latent_ar_notf_h32"])
+def test_latent_rnn_autoregressive_forward(name):
+    """auto_reg=True (the train_inpaintnet.py default), teacher-forced and free-running branches."""
+    fx = load(name)
+    sd = {k: v.clone().requires_grad_(not k.startswith("vae_model.")) for k, v in fx["state_dict"].items()}
+    n_gen = fx["target"].shape[1]
+    w, s, z = O.latent_rnn_forward_autoreg(sd, fx["past"], fx["future"], fx["target"], n_gen, fx["eps_past"],
+                                           fx["eps_future"], fx["eps_target"], fx["eps_regen"], fx["teacher_forcing"])
+    assert torch.equal(s, fx["samples"])
+    assert torch.allclose(z, fx["gen_z"], atol=5e-6, rtol=1e-5)
+    assert torch.allclose(w, fx["weights"], atol=1e-5, rtol=1e-4)
+    loss = O.mean_crossentropy_loss(w, fx["target"])
+    assert abs(loss.item() - fx["loss"]) < 1e-5
+    loss.backward()
+    for k, gg in fx["grads"].items():
+        assert torch.allclose(sd[k].grad, gg, atol=1e-6, rtol=2e-3), k
+
+
 def test_arnn_teacher_forced_logits():
     fx = load("arnn_h32")
     logits = O.arnn_forward_tf(fx["state_dict"], fx["score"], fx["metadata"], fx["constraints_loc"])
