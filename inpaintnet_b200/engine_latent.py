@@ -150,7 +150,11 @@ def latent_forward(arena, prec, model, past, future, n_gen, training, need_grad,
     vae = model.vae_model
     dec = vae.decoder
     dcfg = dec._cfg()
-    Z, Hc, Hg = model.z_dim, model.rnn_hidden_size, model.rnn_hidden_size * model.num_rnn_layers
+    # LatentRNNAblations (latent_rnn_ablations.py:79,143-146): only one context GRU seeds the generation GRU, whose
+    # hidden size is then that of the context GRU
+    only = getattr(model, "type", None)
+    Z, Hc = model.z_dim, model.rnn_hidden_size
+    Hg = Hc if only is not None else Hc * model.num_rnn_layers
     assert model.num_rnn_layers == 2, "the generation GRU initial state only lines up for 2 layers (SURVEY.md a14)"
     B, n_p, _ = past.shape
     n_f = future.shape[1]
@@ -176,7 +180,10 @@ def latent_forward(arena, prec, model, past, future, n_gen, training, need_grad,
         return hs_g[i][l, d].data_ptr() + (es * Tg * B * Hg if d == 1 else 0)
 
     saved_ctx = []
-    for which, (n_m, row0, col0) in (("context_rnn_past.", (n_p, 0, 0)), ("context_rnn_future.", (n_f, n_p * B, Hc))):
+    ctxs = (("context_rnn_past.", (n_p, 0, 0)), ("context_rnn_future.", (n_f, n_p * B, Hc)))
+    if only is not None:   # the other context GRU's output is discarded by the reference: not run at all
+        ctxs = (("context_rnn_past.", (n_p, 0, 0)),) if only == "past" else (("context_rnn_future.", (n_f, n_p * B, 0)),)
+    for which, (n_m, row0, col0) in ctxs:
         hs = torch.empty(2, 2, (n_m + 1) * B, Hc, dtype=act, device=dev)
         hs[:, 0, :B].zero_()
         hs[:, 1, n_m * B:].zero_()
@@ -222,7 +229,7 @@ def latent_forward(arena, prec, model, past, future, n_gen, training, need_grad,
     saved = None
     if need_grad:
         saved = dict(B=B, T=T, n_p=n_p, n_f=n_f, z_ctx=z_ctx, saved_ctx=saved_ctx, steps=steps, step_mode=step_mode,
-                     dcfg=dcfg, Hc=Hc, Hg=Hg, Z=Z)
+                     dcfg=dcfg, Hc=Hc, Hg=Hg, Z=Z, ctx=[(w, c[2]) for w, c in ctxs])
     return weights, samples, z_out, saved
 
 
@@ -281,6 +288,6 @@ def latent_backward(arena, prec, saved, dweights, dz_out):
             bigru2_backward(arena, "generation_rnn.", prec, steps[i]["saved_gen"], dY1=(dY1.data_ptr(), 2 * Hg), dh_n=dh_n,
                             dh0=as_dst(dh0_i))
             dh0 = dh0_i
-    for k, (pfx, col0) in enumerate((("context_rnn_past.", 0), ("context_rnn_future.", Hc))):
+    for k, (pfx, col0) in enumerate(saved["ctx"]):
         bigru2_backward(arena, pfx, prec, saved["saved_ctx"][k],
                         dh_n=[[(dh0[l, d].data_ptr() + 4 * col0, Hg) for d in range(2)] for l in range(2)])

@@ -34,6 +34,9 @@ class _LatentFn(torch.autograd.Function):
 
 
 class LatentRNN(Model):
+    # LatentRNNAblations sets this to "past" / "future": the generation GRU is then seeded by that context GRU only
+    type = None
+
     def __init__(self, dataset, vae_model: MeasureVAE, num_rnn_layers, rnn_hidden_size, dropout, rnn_class,
                  auto_reg=False, teacher_forcing=True):
         super(LatentRNN, self).__init__()
@@ -63,11 +66,11 @@ class LatentRNN(Model):
         else:
             self.gen_rnn_input_dim = 1
             self.x_0 = nn.Parameter(data=torch.randn(1, 1, self.gen_rnn_input_dim))
-        self.generation_rnn = self.rnn_class(input_size=self.gen_rnn_input_dim,
-                                             hidden_size=self.rnn_hidden_size * self.num_rnn_layers,
+        gen_hidden = self.rnn_hidden_size * (self.num_rnn_layers if self.type is None else 1)
+        self.generation_rnn = self.rnn_class(input_size=self.gen_rnn_input_dim, hidden_size=gen_hidden,
                                              num_layers=self.num_rnn_layers, dropout=self.dropout,
                                              bidirectional=self.bidirectional, batch_first=True)
-        self.generation_linear = nn.Linear(2 * self.rnn_hidden_size * self.rnn_num_direction, self.z_dim)
+        self.generation_linear = nn.Linear(gen_hidden * self.rnn_num_direction, self.z_dim)
         self.xavier_initialization()
         cur_dir = os.path.dirname(os.path.realpath(__file__))
         self.filepath = os.path.join(cur_dir, 'models/', self.__repr__())
@@ -82,6 +85,7 @@ class LatentRNN(Model):
 
     def __repr__(self):
         filestr = f'LatentRNN(' \
+                  f'{self.type if self.type is not None else ""}' \
                   f'{self.dataset}' \
                   f'{self.rnn_class},' \
                   f'{self.num_rnn_layers},' \
@@ -130,3 +134,19 @@ class LatentRNN(Model):
             for name, param in mod.named_parameters():
                 if 'weight' in name:
                     nn.init.xavier_normal_(param)
+
+
+class LatentRNNAblations(LatentRNN):
+    """reference: LatentRNN/latent_rnn_ablations.py:11-313 -- the generation GRU (hidden size = the context GRUs',
+    :79) is seeded by the past OR the future context only (:143-146); everything else as LatentRNN.  Both
+    context GRUs are still parameters (same state_dict keys); the unused one receives a zero gradient."""
+
+    def __init__(self, dataset, vae_model: MeasureVAE, num_rnn_layers, rnn_hidden_size, dropout, rnn_class,
+                 auto_reg=False, teacher_forcing=True, type='past'):
+        if type not in ("past", "future"):
+            raise ValueError(type)
+        self.__dict__["type"] = type      # read by LatentRNN.__init__ (sizes) before nn.Module state exists
+        super(LatentRNNAblations, self).__init__(dataset, vae_model, num_rnn_layers, rnn_hidden_size, dropout, rnn_class,
+                                                 auto_reg=auto_reg, teacher_forcing=teacher_forcing)
+        self.type = type
+        # __repr__ (and so the checkpoint file name) is the reference's: 'LatentRNN(' + type + ... (:97-110)

@@ -243,12 +243,13 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=1e-4, b1
 
 def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, num_layers=2,
                        ctx_keep_masks=None, gen_keep_masks=None, dropout_p=0.0, vae_dropout=None,
-                       vae_dropout_p=0.0):
+                       vae_dropout_p=0.0, only=None):
     """Non-autoregressive LatentRNN (auto_reg=False: what the evaluation scripts load,
     test_reconstruction.py:141).  past (B,np,24), future (B,nf,24) int64.
     eps_* (B,n,Z): injected rsample noise (latent_rnn.py:172 samples even in eval).
     Returns weights (B,n_gen,24,V), samples (B,1,24*n_gen), z_out (B,n_gen,Z).
-    The target-encode of latent_rnn.py:133 does not influence any output in this mode."""
+    The target-encode of latent_rnn.py:133 does not influence any output in this mode.
+    only="past"/"future": LatentRNNAblations (latent_rnn_ablations.py:143-146), one context seeds the generation GRU."""
     B = past.shape[0]
     vp = "vae_model."
 
@@ -263,7 +264,7 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
     km = ctx_keep_masks or {}
     _, hp = gru_forward(sd, "context_rnn_past.", zp, h0, num_layers, True, km.get("past"), dropout_p)
     _, hf = gru_forward(sd, "context_rnn_future.", zf, h0, num_layers, True, km.get("future"), dropout_p)
-    ctx = torch.cat((hp, hf), 2)                                               # latent_rnn.py:140
+    ctx = torch.cat((hp, hf), 2) if only is None else (hp if only == "past" else hf)   # latent_rnn.py:140
     x = sd["x_0"].expand(B, n_gen, -1)                                         # latent_rnn.py:228
     out, _ = gru_forward(sd, "generation_rnn.", x, ctx, num_layers, True, gen_keep_masks, dropout_p)
     z_out = linear(out.reshape(B * n_gen, -1), sd["generation_linear.weight"],
@@ -277,7 +278,7 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
 
 
 def latent_rnn_forward_autoreg(sd, past, future, target, n_gen, eps_past, eps_future, eps_target, eps_regen,
-                               teacher_forcing, num_layers=2):
+                               teacher_forcing, num_layers=2, only=None):
     """Autoregressive LatentRNN (auto_reg=True, the train_inpaintnet.py default; latent_rnn.py:142-153,219-261),
     eval-mode dropout.  teacher_forcing=True: the generation GRU reads [z_past[-1], z_target[:-1]] in one call
     (latent_rnn.py:148-149,230-240).  teacher_forcing=False: per gap measure one GRU call of length 1 with the
@@ -297,7 +298,7 @@ def latent_rnn_forward_autoreg(sd, past, future, target, n_gen, eps_past, eps_fu
     h0 = torch.zeros(num_layers * 2, B, Hc, dtype=zp.dtype)
     _, hp = gru_forward(sd, "context_rnn_past.", zp, h0, num_layers, True)
     _, hf = gru_forward(sd, "context_rnn_future.", zf, h0, num_layers, True)
-    hidden = torch.cat((hp, hf), 2)                                            # latent_rnn.py:140
+    hidden = torch.cat((hp, hf), 2) if only is None else (hp if only == "past" else hf)   # latent_rnn.py:140
     lw, lb = sd["generation_linear.weight"], sd["generation_linear.bias"]
     ws, ss = [], []
     if teacher_forcing:

@@ -103,16 +103,23 @@ def adam_case():
     torch.save(dict(p0=p0, grads=grads, ps=ps), os.path.join(HERE, "adam.pt"))
 
 
-def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights, auto_reg=False, teacher_forcing=False):
+def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights, auto_reg=False, teacher_forcing=False,
+                abl_type=None):
     """auto_reg=True: latent_rnn.py:142-153,219-261; teacher_forcing picks the branch (the coin is forced through
     teacher_forcing_prob); eps_regen[i] is the rsample noise of the re-encode after gap measure i (no-TF branch)."""
     ds = FakeDataset(V)
     vae = R.MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
     vsd = recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), seed)
     vae.load_state_dict(vsd)
-    model = R.LatentRNN(ds, vae, 2, Hc, 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg)
+    if abl_type is None:
+        model = R.LatentRNN(ds, vae, 2, Hc, 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg)
+    else:   # latent_rnn_ablations.py: context from one side only, generation GRU hidden size = Hc
+        import importlib
+        abl = importlib.import_module("LatentRNN.latent_rnn_ablations")
+        model = abl.LatentRNNAblations(ds, vae, 2, Hc, 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg,
+                                       type=abl_type)
     model.teacher_forcing_prob = 2.0 if teacher_forcing else -1.0
-    lsd = recipe.make_state_dict(recipe.latent_rnn_spec(Z, Hc, auto_reg=auto_reg), seed + 10)
+    lsd = recipe.make_state_dict(recipe.latent_rnn_spec(Z, Hc, auto_reg=auto_reg, ablation=abl_type is not None), seed + 10)
     sd = dict(lsd)
     sd.update({"vae_model." + k: v for k, v in vsd.items()})
     model.load_state_dict(sd)
@@ -134,7 +141,7 @@ def latent_case(name, V, H, Z, Hc, B, n_past, n_tgt, n_fut, seed, store_weights,
     top2 = weights.detach().topk(2, dim=3).values
     fx = dict(V=V, H=H, Z=Z, Hc=Hc, B=B, seed=seed, past=past, future=future, target=target,
               eps_past=eps_p, eps_future=eps_f, eps_target=eps_t, eps_regen=eps_r, auto_reg=auto_reg,
-              teacher_forcing=teacher_forcing,
+              teacher_forcing=teacher_forcing, abl_type=abl_type,
               weights=weights.detach().clone(), samples=samples.clone(), gen_z=gen_z.detach().clone(),
               loss=loss.item(), acc=acc.item(), margin=(top2[..., 0] - top2[..., 1]).clone(),
               grads=grads_summary(model, store_weights))
@@ -187,6 +194,11 @@ if __name__ == "__main__":
                                                    store_weights=True, auto_reg=True, teacher_forcing=True)),
         ("latent_ar_notf_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=2, n_tgt=3, n_fut=3, seed=828,
                                                      store_weights=True, auto_reg=True, teacher_forcing=False)),
+        ("latent_abl_future_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=2, n_fut=3, seed=900,
+                                                        store_weights=True, abl_type="future")),
+        ("latent_abl_past_ar_tf_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=3, n_fut=2,
+                                                            seed=1000, store_weights=True, auto_reg=True, teacher_forcing=True,
+                                                            abl_type="past")),
     ]
     for name, fn in cases:
         if name.startswith(only):

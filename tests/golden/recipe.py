@@ -48,19 +48,19 @@ def mvae_spec(V, E=10, H=512, Z=256, L=2):
     return s
 
 
-def latent_rnn_spec(Z=256, Hc=512, L=2, auto_reg=False):
+def latent_rnn_spec(Z=256, Hc=512, L=2, auto_reg=False, ablation=False):
     s = {}
     if not auto_reg:
         s["x_0"] = (1, 1, 1)
     for name, I, H in (("context_rnn_past", Z, Hc), ("context_rnn_future", Z, Hc),
-                       ("generation_rnn", Z if auto_reg else 1, Hc * L)):
+                       ("generation_rnn", Z if auto_reg else 1, Hc if ablation else Hc * L)):
         for l in range(L):
             for sfx in ("", "_reverse"):
                 s[f"{name}.weight_ih_l{l}{sfx}"] = (3 * H, I if l == 0 else 2 * H)
                 s[f"{name}.weight_hh_l{l}{sfx}"] = (3 * H, H)
                 s[f"{name}.bias_ih_l{l}{sfx}"] = (3 * H,)
                 s[f"{name}.bias_hh_l{l}{sfx}"] = (3 * H,)
-    s["generation_linear.weight"] = (Z, 2 * Hc * 2)
+    s["generation_linear.weight"] = (Z, 2 * (Hc if ablation else Hc * L))
     s["generation_linear.bias"] = (Z,)
     return s
 

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 from inpaintnet_b200 import engine, functional as Fn
 from inpaintnet_b200.data import SyntheticFolkDataset
-from inpaintnet_b200.latent_rnn import LatentRNN
+from inpaintnet_b200.latent_rnn import LatentRNN, LatentRNNAblations
 from inpaintnet_b200.measure_vae import MeasureVAE
 from tests.golden import recipe
 
@@ -17,7 +17,7 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda"
 
 
-def build(fx, prec, auto_reg=False):
+def build(fx, prec, auto_reg=False, abl_type=None):
     if "state_dict" in fx:
         sd = fx["state_dict"]
     else:
@@ -26,7 +26,11 @@ def build(fx, prec, auto_reg=False):
             recipe.mvae_spec(fx["V"], 10, fx["H"], fx["Z"]), fx["seed"]).items()})
     ds = SyntheticFolkDataset(num_notes=fx["V"])
     vae = MeasureVAE(ds, encoder_hidden_size=fx["H"], decoder_hidden_size=fx["H"], latent_space_dim=fx["Z"])
-    m = LatentRNN(ds, vae, 2, fx["Hc"], 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg)
+    if abl_type is None:
+        m = LatentRNN(ds, vae, 2, fx["Hc"], 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg)
+    else:
+        m = LatentRNNAblations(ds, vae, 2, fx["Hc"], 0.5, torch.nn.GRU, auto_reg=auto_reg, teacher_forcing=auto_reg,
+                               type=abl_type)
     m.load_state_dict(sd)
     m.to(DEV)
     m.set_precision(prec)
@@ -110,24 +114,26 @@ def _ar_noise(fx):
     return eps
 
 
-@pytest.mark.parametrize("name", ["latent_ar_tf_h32", "latent_ar_notf_h32"])
+@pytest.mark.parametrize("name", ["latent_ar_tf_h32", "latent_ar_notf_h32", "latent_abl_past_ar_tf_h32",
+                                  "latent_abl_future_h32"])
 def test_autoregressive_latent_rnn_vs_reference_golden(name):
-    """auto_reg=True (train_inpaintnet.py default): teacher-forced and free-running generation, forward and
-    backward, fp32 mode against the unmodified reference (1e-3 relative; argmax tokens bit-exact)."""
+    """auto_reg=True (train_inpaintnet.py default): teacher-forced and free-running generation, and the
+    LatentRNNAblations variants (one-sided context), forward and backward, fp32 mode against the unmodified
+    reference (1e-3 relative; argmax tokens bit-exact)."""
     fx = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
-    m = build(fx, "fp32", auto_reg=True)
+    m = build(fx, "fp32", auto_reg=fx["auto_reg"], abl_type=fx.get("abl_type"))
     m.eval()
     m.teacher_forcing_prob = 2.0 if fx["teacher_forcing"] else -1.0
     n_t = fx["target"].shape[1]
     m.zero_grad()
-    with engine.inject_noise(eps=_ar_noise(fx)):
+    with engine.inject_noise(eps=_ar_noise(fx) if fx["auto_reg"] else _ar_noise(fx)[:2]):
         weights, samples, gen_z = m(fx["past"].to(DEV), fx["future"].to(DEV), fx["target"].to(DEV), n_t, train=True)
     assert weights.shape == fx["weights"].shape and samples.shape == fx["samples"].shape
     B = fx["past"].shape[0]
     strict = (fx["margin"] > 1e-4).reshape(B, -1)
     same = samples.cpu()[:, 0] == fx["samples"][:, 0]
     assert bool((same | ~strict).all()), "argmax decode differs on a strict-margin row"
-    if not fx["teacher_forcing"]:
+    if fx["auto_reg"] and not fx["teacher_forcing"]:
         assert bool(same.all())   # fixture chosen with min margin 2e-3: a flip would cascade through the re-encode
     assert rel_err(gen_z.detach().cpu(), fx["gen_z"]) < 1e-3
     if not bool(same.all()):
@@ -146,6 +152,9 @@ def test_autoregressive_latent_rnn_vs_reference_golden(name):
         if err > 3e-3:
             bad.append((k, err))
     assert not bad, bad
+    for k, p in params.items():   # what the reference leaves without gradient (frozen VAE, unused context GRU) stays zero
+        if k not in fx["grads"]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
 
 
 @pytest.mark.parametrize("tf", [True, False])

@@ -58,7 +58,7 @@ def test_adam_matches_torch():
         assert torch.allclose(p, pref, atol=1e-7, rtol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["latent_h32", "latent_default"])
+@pytest.mark.parametrize("name", ["latent_h32", "latent_default", "latent_abl_future_h32"])
 def test_latent_rnn_forward(name):
     fx = load(name)
     if "state_dict" in fx:
@@ -70,7 +70,7 @@ def test_latent_rnn_forward(name):
     sd = {k: v.clone().requires_grad_(not k.startswith("vae_model.")) for k, v in sd.items()}
     n_gen = fx["target"].shape[1]
     w, s, z = O.latent_rnn_forward(sd, fx["past"], fx["future"], fx["target"], n_gen,
-                                   fx["eps_past"], fx["eps_future"])
+                                   fx["eps_past"], fx["eps_future"], only=fx.get("abl_type"))
     assert torch.allclose(z, fx["gen_z"], atol=5e-6, rtol=1e-5)
     strict = (fx["margin"] > 1e-4).reshape(s.shape[0], -1)
     same = (s[:, 0] == fx["samples"][:, 0])
@@ -88,14 +88,15 @@ def test_latent_rnn_forward(name):
                 assert torch.allclose(mine, gg, atol=1e-6, rtol=2e-3), k
 
 
-@pytest.mark.parametrize("name", ["latent_ar_tf_h32", "latent_ar_notf_h32"])
+@pytest.mark.parametrize("name", ["latent_ar_tf_h32", "latent_ar_notf_h32", "latent_abl_past_ar_tf_h32"])
 def test_latent_rnn_autoregressive_forward(name):
     """auto_reg=True (the train_inpaintnet.py default), teacher-forced and free-running branches."""
     fx = load(name)
     sd = {k: v.clone().requires_grad_(not k.startswith("vae_model.")) for k, v in fx["state_dict"].items()}
     n_gen = fx["target"].shape[1]
     w, s, z = O.latent_rnn_forward_autoreg(sd, fx["past"], fx["future"], fx["target"], n_gen, fx["eps_past"],
-                                           fx["eps_future"], fx["eps_target"], fx["eps_regen"], fx["teacher_forcing"])
+                                           fx["eps_future"], fx["eps_target"], fx["eps_regen"], fx["teacher_forcing"],
+                                           only=fx.get("abl_type"))
     assert torch.equal(s, fx["samples"])
     assert torch.allclose(z, fx["gen_z"], atol=5e-6, rtol=1e-5)
     assert torch.allclose(w, fx["weights"], atol=1e-5, rtol=1e-4)
