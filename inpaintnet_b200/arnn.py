@@ -32,7 +32,7 @@ def _round8(x):
 def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=False, step=None, table=0, tokptr=0,
                     state=None):
     """Runs a stack of single-layer LSTMs. names[l] = parameter prefix ('lstm_generation.0.').  P0: tensor [T*B,4H]
-    = input projection of layer 0 incl. b_ih.  step=None: whole sequence; step=t: only timestep t (serial decode).
+    = input projection of layer 0 incl. b_ih.  step=None: whole sequence; step=t: only timestep t (serial decode); step=(s0, s1): timesteps [s0, s1).
     Returns the state dict (hseq, cseq, gates, y per layer)."""
     dev, act = P0.device, prec.tdt
     L = len(names)
@@ -42,10 +42,10 @@ def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=F
                      gates=[torch.empty(T * B, 4 * H, dtype=act, device=dev) if need_grad else None for _ in range(L)],
                      y=[torch.empty(T * B, H, dtype=act, device=dev) for _ in range(L)],
                      P=[P0] + [torch.empty(T * B, 4 * H, dtype=act, device=dev) for _ in range(L - 1)])
-    s0, s1 = (0, 0) if step is None else (step, step + 1)
+    s0, s1 = (0, 0) if step is None else (step if isinstance(step, tuple) else (step, step + 1))
     for l, nm in enumerate(names):
         if l > 0:
-            rows, r0 = (T * B, 0) if step is None else (B, step * B)
+            rows, r0 = (T * B, 0) if step is None else ((s1 - s0) * B, s0 * B)
             _lin(prec, state["y"][l - 1].data_ptr() + prec.es * r0 * H, H, rows, H, arena.w(prec, nm + "weight_ih_l0"), 4 * H,
                  state["P"][l].data_ptr() + prec.es * r0 * 4 * H, prec.act, 4 * H, bias=arena.fptr(nm + "bias_ih_l0"))
         ops.lstm_layer_fwd(prec, T, B, H, arena.w(prec, nm + "weight_hh_l0")[0], arena.fptr(nm + "bias_hh_l0"),
@@ -183,8 +183,22 @@ class ConstraintModelGaussianReg(Model):
         gap = (constraints_loc[0, 0, :] == 0).nonzero().squeeze()
         return [logits[:, gap, :]], None
 
+    def forward_inpaint(self, score_tensor, metadata_tensor, constraints_loc, start_tick, end_tick):
+        """Inference: teacher-forced scan of the ticks before the gap, then one tick at a time through the gap
+        [start_tick, end_tick) feeding back the argmax of batch element 0 (arnn_model.py:261-346).
+        -> ([weights (batch, end_tick - start_tick, num_notes)], gen_score (batch, 1, length))"""
+        arena = arena_of(self)
+        prec = Precision(self.precision or Fn.default_precision())
+        start_tick, end_tick = int(start_tick), int(end_tick)
+        if not 0 <= start_tick < end_tick <= score_tensor.shape[2]:
+            raise ValueError(f"forward_inpaint: bad gap [{start_tick}, {end_tick}) for length {score_tensor.shape[2]}")
+        with torch.no_grad():
+            logits, gen = self._engine_forward(arena, prec, score_tensor.long(), metadata_tensor.long(),
+                                               constraints_loc.long(), False, False, inpaint=(start_tick, end_tick))
+        return [logits], gen
+
     # ------------------------------------------------------------------------------------------
-    def _engine_forward(self, arena, prec, score, metadata, cl, teacher_forcing, need_grad):
+    def _engine_forward(self, arena, prec, score, metadata, cl, teacher_forcing, need_grad, inpaint=None):
         ops.require_cuda(score, "score tensor")
         B, _, T = score.shape
         H, E, Em, L = self.num_lstm_constraints_units, self.note_embedding_dim, self.metadata_embedding_dim, self.num_layers
@@ -218,6 +232,8 @@ class ConstraintModelGaussianReg(Model):
         w_c = arena.w(prec, gnames[0] + "weight_ih_l0", E, H)
         Pg = torch.empty(T * B, 4 * H, dtype=act, device=dev)
         saved_in = {}
+        if inpaint is not None:
+            return self._inpaint_generation(arena, prec, score, tok, cout, gnames, w_e, w_c, Pg, inpaint)
         if teacher_forcing:
             # shift-right note embeddings, zero first step, whole-timestep dropout (arnn_model.py:367-373,437-442)
             idx = torch.cat((torch.full((1, B), -1, dtype=torch.int32, device=dev), tok[:-1]), 0).contiguous()
@@ -245,14 +261,7 @@ class ConstraintModelGaussianReg(Model):
             _lin(prec, cout.data_ptr(), H, T * B, H, w_c, 4 * H, Pg.data_ptr(), prec.act, 4 * H,
                  bias=arena.fptr(gnames[0] + "bias_ih_l0"))
 
-            def build_table():
-                tab = torch.empty(V + 1, 4 * H, dtype=torch.float32, device=dev)
-                ops.gemm(CORE_SIMT, F32, V + 1, 4 * H, [(arena.fptr("note_embeddings.0.weight"), E, 0,
-                                                        arena.fptr(gnames[0] + "weight_ih_l0"), E + H, 0, E)],
-                         tab.data_ptr(), F32, 4 * H)
-                return tab
-
-            table = arena.derived(("arnn", "gen_table"), build_table)
+            table = self._gen_table(arena, gnames, dev)
             tokens_in = torch.zeros(T + 1, dtype=torch.int32, device=dev)     # tokens_in[t] = input token of tick t
             hid = torch.empty(T * B, Lh, dtype=act, device=dev)
             logits = torch.empty(B, T, V, dtype=torch.float32, device=dev)
@@ -273,6 +282,71 @@ class ConstraintModelGaussianReg(Model):
             saved = dict(B=B, T=T, Xc=Xc, ldc=ldc, Ic=Ic, md_f=md_f, masked_f=masked_f, cstate=cstate, gstate=gstate, cout=cout,
                          hid=hid, tf=teacher_forcing, **saved_in)
         return logits, saved
+
+    def _gen_table(self, arena, gnames, dev, zero_row=False):
+        """table[v] = note_embedding[v] @ W_ih[:, :E]^T of the first generation LSTM (gathered by the fed-back token);
+        zero_row: one extra all-zero row (id V+1 = 'no token term')."""
+        H, E, V = self.num_lstm_constraints_units, self.note_embedding_dim, self.num_notes_per_voice[0]
+
+        def build_table():
+            tab = torch.zeros(V + 2 if zero_row else V + 1, 4 * H, dtype=torch.float32, device=dev)
+            ops.gemm(CORE_SIMT, F32, V + 1, 4 * H, [(arena.fptr("note_embeddings.0.weight"), E, 0,
+                                                    arena.fptr(gnames[0] + "weight_ih_l0"), E + H, 0, E)],
+                     tab.data_ptr(), F32, 4 * H)
+            return tab
+
+        return arena.derived(("arnn", "gen_table_z" if zero_row else "gen_table"), build_table)
+
+    def _inpaint_generation(self, arena, prec, score, tok, cout, gnames, w_e, w_c, Pg, inpaint):
+        """arnn_model.py:287-346.  The hoisted input projection covers both regimes: rows < start carry the
+        shifted ground-truth embedding (with the whole-timestep input dropout in train mode, :291), row `start`
+        the undropped embedding of score[start-1] (per batch element, :318), rows > start only the constraint part
+        -- their token term is the fed-back argmax of batch element 0, gathered from the table inside the step kernel."""
+        B, _, T = score.shape
+        H, E, L = self.num_lstm_constraints_units, self.note_embedding_dim, self.num_layers
+        V, Lh = self.num_notes_per_voice[0], self.num_units_linear
+        dev, act, es = score.device, prec.tdt, prec.es
+        s0, s1 = inpaint
+        idx = torch.cat((torch.full((1, B), -1, dtype=torch.int32, device=dev), tok[:-1]), 0)
+        idx[s0 + 1:] = -1
+        if s0 == 0:
+            idx[0] = -1
+        idx = idx.contiguous()
+        scale = None
+        if self.training and self.dropout_input_prob > 0:
+            keep = NOISE.keep_mask(arena, (T * B,), self.dropout_input_prob, dev)
+            scale = keep.to(torch.float32) / (1.0 - self.dropout_input_prob)
+            scale[s0 * B:] = 1.0
+        Xe = torch.zeros(T * B, 16, dtype=act, device=dev)
+        ops.gather_cols(arena.fptr("note_embeddings.0.weight"), E, idx.data_ptr(), 1, T * B, Xe.data_ptr(), prec.act, 16, 0,
+                        row_scale=scale.data_ptr() if scale is not None else 0)
+        ops.gemm(prec.core, prec.act, T * B, 4 * H,
+                 [(Xe.data_ptr(), 16, 0, w_e[0], w_e[1], 0, E), (cout.data_ptr(), H, 0, w_c[0], w_c[1], 0, H)],
+                 Pg.data_ptr(), prec.act, 4 * H, bias=arena.fptr(gnames[0] + "bias_ih_l0"))
+        gstate = None
+        if s0 > 0:
+            gstate = _lstm_stack_fwd(arena, prec, gnames, Pg, T, B, H, False, step=(0, s0))
+        table = self._gen_table(arena, gnames, dev, zero_row=True)
+        tokens_in = torch.zeros(T + 1, dtype=torch.int32, device=dev)     # tokens_in[t] = token fed at tick t
+        if s0 > 0:
+            tokens_in[s0] = V + 1        # tick `start`: the token term is already in Pg (per batch element)
+        n = s1 - s0
+        hid = torch.empty(n * B, Lh, dtype=act, device=dev)
+        logits = torch.empty(B, n, V, dtype=torch.float32, device=dev)
+        w1, wo = arena.w(prec, "linear_1.weight"), arena.w(prec, "linear_ouput_notes.0.weight")
+        for t in range(s0, s1):
+            gstate = _lstm_stack_fwd(arena, prec, gnames, Pg, T, B, H, False, step=t, table=table.data_ptr(),
+                                     tokptr=tokens_in.data_ptr() + 4 * t, state=gstate)
+            yo = gstate["y"][L - 1].data_ptr() + es * t * B * H
+            k = t - s0
+            _lin(prec, yo, H, B, H, w1, Lh, hid.data_ptr() + es * k * B * Lh, prec.act, Lh, bias=arena.fptr("linear_1.bias"),
+                 act=ACT_RELU)
+            _lin(prec, hid.data_ptr() + es * k * B * Lh, Lh, B, Lh, wo, V, logits.data_ptr() + 4 * k * V, F32, n * V,
+                 bias=arena.fptr("linear_ouput_notes.0.bias"))
+            ops.argmax_rows(logits.data_ptr() + 4 * k * V, 1, V, tok_out=tokens_in.data_ptr() + 4 * (t + 1))
+        gen = score.clone()
+        gen[:, 0, s0:s1] = tokens_in[s0 + 1:s1 + 1].to(torch.int64)[None, :]
+        return logits, gen
 
     def _engine_backward(self, arena, prec, sv, dlogits):
         B, T = sv["B"], sv["T"]

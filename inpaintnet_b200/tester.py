@@ -72,3 +72,85 @@ class LatentRNNTester(object):
         print('Test Epoch:')
         print('\tTest Loss: ', mean_loss / n, '\n\tTest Accuracy: ', mean_acc / n * 100)
         return mean_loss / n, mean_acc / n
+
+
+class AnticipationRNNTester(object):
+    """Held-out inpainting loss / accuracy of the AnticipationRNN baseline
+    (AnticipationRNN/anticipation_rnn_tester.py:20-86,245-356): every test batch is inpainted over a fixed gap
+    (2 measures starting at measure 8) with ConstraintModelGaussianReg.forward_inpaint."""
+
+    def __init__(self, dataset, model):
+        self.dataset = dataset
+        self.model = model
+        self.model.eval()
+        self.batch_size = 1
+        self.measure_seq_len = 24
+
+    def test_model(self, batch_size=512):
+        (_, _, gen_test) = self.dataset.data_loaders(batch_size=batch_size, split=(0.01, 0.01))
+        print('Num Test Batches: ', len(gen_test))
+        mean_loss_test, mean_accuracy_test = self.loss_and_acc_test(gen_test)
+        print('Test Epoch: 1/1')
+        print(f'\tTest Loss: {mean_loss_test}\tTest Accuracy: {mean_accuracy_test * 100} %')
+        return mean_loss_test, mean_accuracy_test
+
+    def loss_and_acc_test(self, data_loader):
+        mean_loss, mean_accuracy, n = 0, 0, 0
+        for batch in data_loader:
+            score, metadata, constraints_loc, start_tick, end_tick = self.process_batch_data(batch)
+            weights, _ = self.model.forward_inpaint(score_tensor=score, metadata_tensor=metadata,
+                                                    constraints_loc=constraints_loc, start_tick=start_tick,
+                                                    end_tick=end_tick)
+            targets = score[:, :, start_tick:end_tick].transpose(0, 1)      # (num_voices, batch, gap ticks)
+            mean_loss += to_numpy(self.mean_crossentropy_loss(weights, targets))
+            mean_accuracy += to_numpy(self.mean_accuracy(weights, targets))
+            n += 1
+        n = max(n, 1)
+        return mean_loss / n, mean_accuracy / n
+
+    def process_batch_data(self, batch):
+        tensor_score, tensor_metadata = batch
+        tensor_score = to_cuda_variable_long(tensor_score)
+        tensor_metadata = to_cuda_variable_long(tensor_metadata)
+        constraints_location, start_tick, end_tick = self.get_constraints_location(tensor_score, is_stochastic=False)
+        return tensor_score, tensor_metadata, constraints_location, start_tick, end_tick
+
+    def get_constraints_location(self, tensor_score, is_stochastic, start_measure=None, num_measures=None):
+        """-> constraints (1 = given, 0 = to inpaint) shaped like tensor_score, start_tick, end_tick.
+        Stochastic: gap of 2..n-11 measures with at least 5 measures of context on both sides
+        (anticipation_rnn_tester.py:278-303); otherwise measures [8, 10) unless told otherwise (:304-308)."""
+        ticks = self.dataset.subdivision * self.dataset.num_beats_per_bar
+        if is_stochastic:
+            n = int(tensor_score.size(2) / ticks)
+            assert n == self.dataset.n_bars
+            num_target = int(torch.randint(low=2, high=n - 10, size=(1,)).item())
+            num_past = int(torch.randint(low=5, high=n - num_target - 5, size=(1,)).item())
+            assert n - num_past - num_target >= 5
+            start_measure, num_measures = num_past + 1, num_target
+        else:
+            start_measure = 8 if start_measure is None else start_measure
+            num_measures = 2 if num_measures is None else num_measures
+        start_tick = start_measure * ticks
+        end_tick = start_tick + num_measures * ticks
+        constraints_location = torch.zeros_like(tensor_score)
+        if start_tick > 0:
+            constraints_location[:, :, :start_tick] = 1
+        if end_tick < constraints_location.size(2) - 1:
+            constraints_location[:, :, end_tick:] = 1
+        return constraints_location, start_tick, end_tick
+
+    @staticmethod
+    def mean_crossentropy_loss(weights, targets):
+        """weights: list (per voice) of (batch, seq_len, num_notes); targets (num_voices, batch, seq_len)"""
+        total = 0
+        for i, w in enumerate(weights):
+            total = total + Fn.fused_ce_kl(w, targets[i])[0]
+        return total / len(weights)
+
+    @staticmethod
+    def mean_accuracy(weights, targets):
+        total = 0
+        with torch.no_grad():
+            for i, w in enumerate(weights):
+                total = total + Fn.fused_ce_kl(w.detach(), targets[i])[1]
+        return total / len(weights)

@@ -420,3 +420,47 @@ def arnn_forward_no_tf(sd, score, metadata, constraints_loc, num_layers=2):
         outs.append(w)
         cur = int(torch.argmax(w[0].detach()))
     return torch.stack(outs, 1), torch.tensor(fed)
+
+
+def arnn_forward_inpaint(sd, score, metadata, constraints_loc, start_tick, end_tick, num_layers=2):
+    """AnticipationRNN inpainting inference (arnn_model.py:261-346), one voice, eval mode (no input dropout).
+    Ticks [0, start) run teacher forced (input = embedding of score[t-1], zeros at t = 0, :286-299); ticks
+    [start, end) run one at a time: the input token of tick `start` is score[start-1] per batch element, later
+    ticks feed back the argmax of batch element 0 to the whole batch (:318-343).
+    Returns logits (B, end-start, V) and the generated score (B,1,T)."""
+    B, _, T = score.shape
+    tok = score[:, 0]
+    emb_w = sd["note_embeddings.0.weight"]
+    V1 = emb_w.shape[0]
+    masked = torch.where(constraints_loc[:, 0] > 0, tok, torch.full_like(tok, V1 - 1))
+    md = metadata[:, 0]
+    embs_m = [sd[f"metadata_embeddings.{k}.weight"][md[:, :, k]] for k in range(md.shape[-1])]
+    x = torch.flip(torch.cat(embs_m + [emb_w[masked]], 2), [1])
+    for l in range(num_layers):
+        x = lstm_layer(x, sd[f"lstm_constraint.{l}.weight_ih_l0"], sd[f"lstm_constraint.{l}.weight_hh_l0"],
+                       sd[f"lstm_constraint.{l}.bias_ih_l0"], sd[f"lstm_constraint.{l}.bias_hh_l0"])
+    cout = torch.flip(x, [1])
+    H = cout.shape[2]
+    hs = [torch.zeros(B, H, dtype=cout.dtype) for _ in range(num_layers)]
+    cs = [torch.zeros(B, H, dtype=cout.dtype) for _ in range(num_layers)]
+
+    def step(note_emb, t):
+        inp = torch.cat((note_emb, cout[:, t]), 1)
+        for l in range(num_layers):
+            xp = inp @ sd[f"lstm_generation.{l}.weight_ih_l0"].t() + sd[f"lstm_generation.{l}.bias_ih_l0"]
+            hs[l], cs[l] = lstm_cell(xp, hs[l], cs[l], sd[f"lstm_generation.{l}.weight_hh_l0"], sd[f"lstm_generation.{l}.bias_hh_l0"])
+            inp = hs[l]
+        return inp
+
+    for t in range(start_tick):                                               # arnn_model.py:286-299
+        step(emb_w[tok[:, t - 1]] if t > 0 else torch.zeros(B, emb_w.shape[1], dtype=cout.dtype), t)
+    gen = score.clone()
+    outs = []
+    for t in range(start_tick, end_tick):                                     # arnn_model.py:304-343
+        prev = gen[:, 0, t - 1] if t > 0 else torch.zeros(B, dtype=torch.long)
+        out = step(emb_w[prev], t)
+        w = linear(torch.relu(linear(out, sd["linear_1.weight"], sd["linear_1.bias"])),
+                   sd["linear_ouput_notes.0.weight"], sd["linear_ouput_notes.0.bias"])
+        outs.append(w)
+        gen[:, 0, t] = int(torch.argmax(w[0]))
+    return torch.stack(outs, 1), gen

@@ -178,6 +178,33 @@ def arnn_case(name, V, B, seed):
     print(name, weights[0].shape)
 
 
+def arnn_inpaint_case(name, V, B, seed, start, end):
+    """ConstraintModelGaussianReg.forward_inpaint (arnn_model.py:261-346): prefix scan + per-tick generation."""
+    ds = FakeDataset(V)
+    random.seed(seed)
+    torch.manual_seed(seed)
+    model = R.ConstraintModelGaussianReg(
+        dataset=ds, note_embedding_dim=10, metadata_embedding_dim=2, num_lstm_constraints_units=32,
+        num_lstm_generation_units=32, linear_hidden_size=32, num_layers=2, dropout_input_prob=0.2,
+        dropout_prob=0.2, unary_constraint=True, teacher_forcing=True)
+    model.eval()
+    T = 8 * 24
+    score = recipe.make_tokens(B, T, V, seed + 1).view(B, 1, T)
+    t = torch.arange(T)
+    metadata = torch.stack([(t // 6) % 4 == 0, t % 6, torch.zeros_like(t)], 1).long()
+    metadata = metadata.view(1, 1, T, 3).expand(B, 1, T, 3).contiguous()
+    cl = torch.ones(B, 1, T).long()
+    cl[:, :, start:end] = 0
+    with torch.no_grad():
+        w, gen = model.forward_inpaint(score, metadata, cl, start, end)
+    top2 = w[0][0].topk(2, dim=1).values      # the fed-back token is the argmax of batch element 0
+    fx = dict(V=V, B=B, score=score, metadata=metadata, constraints_loc=cl, start=start, end=end,
+              state_dict={k: v.clone() for k, v in model.state_dict().items()},
+              logits=w[0].detach().clone(), gen=gen.clone(), margin=(top2[:, 0] - top2[:, 1]).clone())
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, w[0].shape, "min margin", fx["margin"].min().item())
+
+
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else ""   # optional name prefix: regenerate just those fixtures
     cases = [
@@ -199,6 +226,7 @@ if __name__ == "__main__":
         ("latent_abl_past_ar_tf_h32", lambda n: latent_case(n, V=20, H=32, Z=16, Hc=32, B=3, n_past=3, n_tgt=3, n_fut=2,
                                                             seed=1000, store_weights=True, auto_reg=True, teacher_forcing=True,
                                                             abl_type="past")),
+        ("arnn_inpaint_h32", lambda n: arnn_inpaint_case(n, V=20, B=3, seed=1100, start=3 * 24, end=5 * 24)),
     ]
     for name, fn in cases:
         if name.startswith(only):

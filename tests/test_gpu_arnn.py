@@ -88,3 +88,57 @@ def test_no_teacher_forcing_backward_runs_and_matches_oracle():
         g_ref = sd[k].grad
         err = (p.grad.cpu() - g_ref).abs().max().item() / max(g_ref.abs().max().item(), 1e-8)
         assert err < 3e-3, (k, err)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_forward_inpaint_vs_reference_golden(prec):
+    """forward_inpaint (arnn_model.py:261-346): teacher-forced prefix scan, then per-tick generation through the gap."""
+    fx = torch.load(os.path.join(G, "arnn_inpaint_h32.pt"), weights_only=False)
+    m = build(fx, prec)
+    score, md, cl = fx["score"].to(DEV), fx["metadata"].to(DEV), fx["constraints_loc"].to(DEV)
+    weights, gen = m.forward_inpaint(score, md, cl, fx["start"], fx["end"])
+    assert weights[0].shape == fx["logits"].shape and gen.shape == fx["gen"].shape
+    if prec == "fp32":
+        assert torch.equal(gen.cpu(), fx["gen"])                      # argmax tokens bit-exact (min margin 8e-3)
+        assert rel_err(weights[0].cpu(), fx["logits"]) < 1e-3
+    else:
+        same = (gen.cpu() == fx["gen"])[0, 0, fx["start"]:fx["end"]]
+        n_ok = int(same.long().cumprod(0).sum())                      # ticks before the first differing fed-back token
+        assert n_ok >= 1
+        assert rel_err(weights[0].cpu()[:, :n_ok], fx["logits"][:, :n_ok]) < 3e-2
+    # outside the gap the score is returned untouched
+    assert torch.equal(gen.cpu()[:, :, :fx["start"]], fx["score"][:, :, :fx["start"]])
+    assert torch.equal(gen.cpu()[:, :, fx["end"]:], fx["score"][:, :, fx["end"]:])
+
+
+def test_forward_inpaint_gap_at_start():
+    """start_tick = 0: no prefix; the first input is the start symbol (id 0) as in _forward_no_tf."""
+    fx = torch.load(os.path.join(G, "arnn_inpaint_h32.pt"), weights_only=False)
+    m = build(fx, "fp32")
+    cl = torch.ones_like(fx["constraints_loc"])
+    cl[:, :, :24] = 0
+    weights, gen = m.forward_inpaint(fx["score"].to(DEV), fx["metadata"].to(DEV), cl.to(DEV), 0, 24)
+    logits, gen_ref = O.arnn_forward_inpaint(fx["state_dict"], fx["score"], fx["metadata"], cl, 0, 24)
+    assert torch.equal(gen.cpu(), gen_ref)
+    assert rel_err(weights[0].cpu(), logits) < 1e-3
+
+
+def test_tester_inpainting_loss_matches_oracle():
+    """AnticipationRNNTester.loss_and_acc_test (anticipation_rnn_tester.py:44-86): fixed gap = measures [8, 10)."""
+    from inpaintnet_b200.tester import AnticipationRNNTester
+    fx = torch.load(os.path.join(G, "arnn_inpaint_h32.pt"), weights_only=False)
+    m = build(fx, "fp32")
+    ds = SyntheticFolkDataset(num_notes=fx["V"], num_sequences=6, seed=3)
+    tester = AnticipationRNNTester(ds, m)
+    loader = ds.data_loaders(batch_size=3, split=(0.0, 0.0))[2]
+    loss, acc = tester.loss_and_acc_test(loader)
+    ref_loss, n = 0.0, 0
+    for score, md in loader:
+        cl, s0, s1 = tester.get_constraints_location(score.long(), is_stochastic=False)
+        assert (s0, s1) == (8 * 24, 10 * 24)
+        logits, _ = O.arnn_forward_inpaint(fx["state_dict"], score.long(), md.long(), cl, s0, s1)
+        ref_loss += O.mean_crossentropy_loss(logits, score.long()[:, 0, s0:s1]).item()
+        n += 1
+    assert n == 2
+    assert abs(float(loss) - ref_loss / n) < 1e-3
+    assert 0.0 <= float(acc) <= 1.0

@@ -128,12 +128,12 @@ def test_latent_rnn_plumbing_dry_run(prec):
     assert a.n_trainable < a.total and a.names[0] == "x_0"
 
 
-def test_reference_train_script_runs_unchanged_against_dropin():
-    """The reference's own train_measure_vae.py, unmodified, imported with inpaintnet_b200/dropin first on
-    sys.path (stub library: plumbing only).  Needs /root/reference, so it runs in the build container."""
+def _run_reference_script(script, **kwargs):
+    """Imports /root/reference/<script> UNMODIFIED with inpaintnet_b200/dropin first on sys.path and calls its
+    click main() body under the stub library (plumbing only: argument wiring, shapes, state_dict / checkpoint files)."""
     import importlib.util
     import sys
-    ref = "/root/reference/train_measure_vae.py"
+    ref = "/root/reference/" + script
     if not os.path.exists(ref) or torch.cuda.is_available():
         pytest.skip("reference tree not mounted (or GPU box)")
     dropin = os.path.join(ROOT, "inpaintnet_b200", "dropin")
@@ -143,7 +143,7 @@ def test_reference_train_script_runs_unchanged_against_dropin():
         del sys.modules[m]
     sys.path.insert(0, dropin)
     try:
-        spec = importlib.util.spec_from_file_location("ref_train_measure_vae", ref)
+        spec = importlib.util.spec_from_file_location("ref_" + script[:-3], ref)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         import inpaintnet_b200.data as D
@@ -157,11 +157,7 @@ def test_reference_train_script_runs_unchanged_against_dropin():
         D.SyntheticFolkDataset.__init__ = small
         try:
             with stubbed():
-                mod.main.callback(note_embedding_dim=10, metadata_embedding_dim=2, num_encoder_layers=2,
-                                  encoder_hidden_size=32, encoder_dropout_prob=0.5, has_metadata=False,
-                                  latent_space_dim=16, num_decoder_layers=2, decoder_hidden_size=32,
-                                  decoder_dropout_prob=0.5, batch_size=2, num_epochs=1, train=True, plot=False,
-                                  log=False, lr=1e-4)
+                mod.main.callback(**kwargs)
         finally:
             D.SyntheticFolkDataset.__init__ = orig
     finally:
@@ -169,6 +165,37 @@ def test_reference_train_script_runs_unchanged_against_dropin():
         for m in [k for k in sys.modules if k.split(".")[0] in tops]:
             del sys.modules[m]
         sys.modules.update(saved_mods)
+
+
+_VAE_KW = dict(note_embedding_dim=10, metadata_embedding_dim=2, num_encoder_layers=2, encoder_hidden_size=32,
+               encoder_dropout_prob=0.5, has_metadata=False, latent_space_dim=16, num_decoder_layers=2,
+               decoder_hidden_size=32, decoder_dropout_prob=0.5)
+
+
+def test_reference_train_script_runs_unchanged_against_dropin():
+    """The reference's own train_measure_vae.py, unmodified.  Needs /root/reference (build container only)."""
+    _run_reference_script("train_measure_vae.py", batch_size=2, num_epochs=1, train=True, plot=False, log=False, lr=1e-4,
+                          **_VAE_KW)
+
+
+@pytest.mark.parametrize("auto_reg,teacher_forcing", [(True, True), (True, False), (False, False)])
+def test_reference_train_inpaintnet_runs_unchanged_against_dropin(auto_reg, teacher_forcing):
+    """train_inpaintnet.py, unmodified, at its defaults (auto_reg=True, teacher_forcing=True, :53-56) and the two
+    other generation modes; loads the MeasureVAE checkpoint the previous script saved (vae_model.load(), :113)."""
+    _run_reference_script("train_measure_vae.py", batch_size=2, num_epochs=1, train=True, plot=False, log=False, lr=1e-4,
+                          **_VAE_KW)
+    _run_reference_script("train_inpaintnet.py", num_latent_rnn_layers=2, latent_rnn_hidden_size=32,
+                          latent_rnn_dropout_prob=0.5, batch_size=2, num_epochs=1, train=True, lr=1e-4, plot=False,
+                          log=False, auto_reg=auto_reg, teacher_forcing=teacher_forcing, early_stop=True, **_VAE_KW)
+
+
+@pytest.mark.parametrize("script", ["train_arnn_reg.py", "train_arnn_baseline.py"])
+def test_reference_train_arnn_runs_unchanged_against_dropin(script):
+    """train_arnn_reg.py / train_arnn_baseline.py, unmodified: trainer epoch, then AnticipationRNNTester.test_model
+    (forward_inpaint over the held-out split)."""
+    _run_reference_script(script, note_embedding_dim=10, metadata_embedding_dim=2, num_layers=2, lstm_hidden_size=32,
+                          dropout_lstm=0.2, input_dropout=0.2, linear_hidden_size=32, batch_size=2, num_epochs=1,
+                          train=True, log=False, lr=1e-4, plot=False, teacher_forcing=True, early_stop=True)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

@@ -119,3 +119,11 @@ def test_arnn_no_teacher_forcing_logits():
     # gen_chorale[:, 0, t+1] holds the token fed at tick t+1 (the last argmax is never fed)
     assert torch.equal(fed[1:], fx["gen_no_tf"][0, 0, 1:fed.numel()])
     assert torch.allclose(logits, fx["logits_no_tf"], atol=5e-6, rtol=1e-5)
+
+
+def test_arnn_forward_inpaint():
+    fx = load("arnn_inpaint_h32")
+    logits, gen = O.arnn_forward_inpaint(fx["state_dict"], fx["score"], fx["metadata"], fx["constraints_loc"],
+                                         fx["start"], fx["end"])
+    assert torch.equal(gen, fx["gen"])
+    assert torch.allclose(logits, fx["logits"], atol=2e-6, rtol=1e-5)
