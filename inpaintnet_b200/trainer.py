@@ -8,6 +8,7 @@ loss_and_acc_on_epoch, overridable zero_grad/step) and MeasureVAE/vae_trainer.py
     the NaN / token-range guards are device flags polled with that same sync.
 """
 import os
+import random
 import time
 import datetime
 from abc import ABC, abstractmethod
@@ -39,7 +40,47 @@ class Trainer(ABC):
             self.early_stopper = EarlyStopping()
         self.check_flags_every = 1
 
-    def train_model(self, batch_size, num_epochs, plot=False, log=False):
+    # ---- true resume (absent in the reference): everything a bit-for-bit
+    # continuation needs beyond the weights -- Adam moments + step, epoch, early-stopping state and the RNG streams
+    # (torch seed + the arena's Philox offset drive dropout / eps on the device; python `random` drives the
+    # teacher-forcing coin; the torch CPU generator drives the past/gap/future split and the loader shuffle).
+    def training_state_path(self):
+        return self.model.filepath + '.train_state'
+
+    def training_state(self, epoch_index):
+        a = arena_of(self.model)
+        st = dict(epoch=int(epoch_index), model=self.model.state_dict(), optimizer=self.optimizer.state_dict(),
+                  rng_offset=int(a.rng_offset), torch_seed=int(torch.initial_seed()), torch_rng=torch.get_rng_state(),
+                  python_rng=random.getstate())
+        if self.early_stopping:
+            es = self.early_stopper
+            st["early_stopping"] = dict(counter=es.counter, best_score=es.best_score, early_stop=es.early_stop,
+                                        val_loss_min=es.val_loss_min)
+        return st
+
+    def save_training_state(self, epoch_index, path=None):
+        path = path or self.training_state_path()
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save(self.training_state(epoch_index), tmp)
+        os.replace(tmp, path)          # a killed job never leaves a half-written state behind
+        return path
+
+    def load_training_state(self, path=None):
+        """Restores a state written by save_training_state; returns the index of the next epoch to run."""
+        st = torch.load(path or self.training_state_path(), map_location="cpu", weights_only=False)
+        self.model.load_state_dict(st["model"])
+        self.optimizer.load_state_dict(st["optimizer"])
+        torch.manual_seed(st["torch_seed"])
+        torch.set_rng_state(st["torch_rng"])
+        random.setstate(st["python_rng"])
+        arena_of(self.model).rng_offset = st["rng_offset"]
+        if self.early_stopping and "early_stopping" in st:
+            for k, v in st["early_stopping"].items():
+                setattr(self.early_stopper, k, v)
+        return st["epoch"] + 1
+
+    def train_model(self, batch_size, num_epochs, plot=False, log=False, resume=False):
         if log:
             try:
                 from tensorboard_logger import configure, log_value
@@ -54,7 +95,11 @@ class Trainer(ABC):
         (generator_train, generator_val, _) = self.dataset.data_loaders(batch_size=batch_size, split=(0.70, 0.20))
         print('Num Train Batches: ', len(generator_train))
         print('Num Valid Batches: ', len(generator_val))
-        for epoch_index in range(num_epochs):
+        first_epoch = 0
+        if resume and os.path.exists(self.training_state_path()):
+            first_epoch = self.load_training_state()
+            print(f'Resuming at epoch {first_epoch + 1}/{num_epochs}')
+        for epoch_index in range(first_epoch, num_epochs):
             self.update_scheduler(epoch_index)
             self.model.train()
             mean_loss_train, mean_accuracy_train = self.loss_and_acc_on_epoch(
@@ -75,6 +120,7 @@ class Trainer(ABC):
                 self.model.save()
                 if epoch_index > 0 and epoch_index % 10 == 0:
                     self.model.save_checkpoint(epoch_index)
+                self.save_training_state(epoch_index)
             if self.early_stopping:
                 self.early_stopper(mean_loss_val, self.model)
                 if self.early_stopper.early_stop:

@@ -88,3 +88,65 @@ def test_embedding_gather_and_scatter():
     torch.cuda.synchronize()
     ref = torch.zeros(V + 1, E, device=DEV).index_add_(0, tok.long(), dX[:, :E])
     assert torch.allclose(demb, ref[:V], atol=1e-4) and torch.allclose(dskip, ref[V], atol=1e-4)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_training_resume_continues_the_same_trajectory(prec, tmp_path):
+    """4 train steps (dropout + teacher-forcing coin live) == 2 steps, save_training_state, fresh process state,
+    load_training_state, 2 steps.  Split-K weight gradients use fp32 atomics, so 'same' is to rounding; resuming
+    WITHOUT the saved RNG streams is the control that must differ."""
+    import random
+    from inpaintnet_b200.data import SyntheticFolkDataset
+    from inpaintnet_b200.measure_vae import MeasureVAE
+    from inpaintnet_b200.trainer import VAETrainer
+    from inpaintnet_b200.arena import arena_of
+    V, H, Z, B = 20, 64, 32, 128
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randint(0, V, (B, 24), generator=g).to(DEV) for _ in range(4)]
+
+    def make():
+        torch.manual_seed(21)
+        random.seed(21)
+        ds = SyntheticFolkDataset(num_notes=V)
+        m = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
+        m.to(DEV).set_precision(prec).train()
+        return m, VAETrainer(ds, m, lr=1e-3)
+
+    def steps(tr, bs):
+        out = []
+        for b in bs:
+            tr.zero_grad()
+            loss, _ = tr.loss_and_acc_for_batch(b, 0, train=True)
+            loss.backward()
+            tr.step()
+            out.append(loss.item())
+        return out
+
+    m_a, tr_a = make()
+    losses_a = steps(tr_a, batches)
+    m_b, tr_b = make()
+    losses_b = steps(tr_b, batches[:2])
+    path = tr_b.save_training_state(0, str(tmp_path / "s.pt"))
+    torch.manual_seed(777)      # a new process would start from unrelated RNG state
+    random.seed(777)
+    ds = SyntheticFolkDataset(num_notes=V)
+    m_c = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
+    m_c.to(DEV).set_precision(prec).train()
+    tr_c = VAETrainer(ds, m_c, lr=1e-3)
+    assert tr_c.load_training_state(path) == 1
+    losses_c = steps(tr_c, batches[2:])
+    tol = 1e-4 if prec == "fp32" else 2e-2
+    assert max(abs(x - y) for x, y in zip(losses_a, losses_b + losses_c)) < tol, (losses_a, losses_b + losses_c)
+    pa, pc = arena_of(m_a).flat, arena_of(m_c).flat
+    assert (pa - pc).abs().mean().item() < (1e-5 if prec == "fp32" else 5e-4)
+    # control: same weights and moments, RNG streams NOT restored -> other dropout masks / eps
+    torch.manual_seed(777)
+    random.seed(777)
+    m_d = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
+    m_d.to(DEV).set_precision(prec).train()
+    tr_d = VAETrainer(ds, m_d, lr=1e-3)
+    st = torch.load(path, weights_only=False)
+    m_d.load_state_dict(st["model"])
+    tr_d.optimizer.load_state_dict(st["optimizer"])
+    losses_d = steps(tr_d, batches[2:])
+    assert max(abs(x - y) for x, y in zip(losses_a[2:], losses_d)) > 10 * tol

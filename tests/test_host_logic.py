@@ -224,3 +224,49 @@ def test_arnn_plumbing_dry_run(prec, tf):
         tr.step()
     for n, p in m.named_parameters():
         assert p.grad is not None, n
+
+
+def test_training_state_round_trip(tmp_path):
+    """Trainer.save_training_state / load_training_state: weights, Adam moments + step, RNG streams, early stopping."""
+    if torch.cuda.is_available():
+        pytest.skip("dry run is a CPU-only plumbing check")
+    import random
+    from inpaintnet_b200.trainer import VAETrainer
+    V, H, Z, B = 20, 32, 16, 4
+
+    def make():
+        ds = SyntheticFolkDataset(num_notes=V)
+        m = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z).set_precision("fp32")
+        return m, VAETrainer(ds, m)
+
+    torch.manual_seed(5)
+    random.seed(5)
+    m, tr = make()
+    tr.early_stopping, tr.early_stopper = True, __import__("inpaintnet_b200.trainer", fromlist=["x"]).EarlyStopping()
+    tokens = torch.randint(0, V, (B, 24))
+    with stubbed():
+        m.train()
+        tr.zero_grad()
+        loss, _ = tr.loss_and_acc_for_batch(tokens, 0, train=True)
+        loss.backward()
+        tr.step()
+    tr.optimizer._m.normal_()
+    tr.optimizer._v.uniform_()
+    tr.early_stopper(1.5, m)
+    tr.early_stopper(1.7, m)
+    path = tr.save_training_state(3, str(tmp_path / "state.pt"))
+    want = dict(rng_offset=arena_of(m).rng_offset, py=random.random(), t=torch.rand(3))
+    assert want["rng_offset"] > 0
+    torch.manual_seed(99)
+    random.seed(99)
+    m2, tr2 = make()
+    tr2.early_stopping, tr2.early_stopper = True, type(tr.early_stopper)()
+    assert tr2.load_training_state(path) == 4
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert tr2.optimizer.step_count == 1
+    assert torch.equal(tr2.optimizer._m, tr.optimizer._m) and torch.equal(tr2.optimizer._v, tr.optimizer._v)
+    assert arena_of(m2).rng_offset == want["rng_offset"]
+    assert random.random() == want["py"] and torch.equal(torch.rand(3), want["t"])
+    assert (tr2.early_stopper.counter, tr2.early_stopper.best_score) == (tr.early_stopper.counter, tr.early_stopper.best_score)
+    assert not os.path.exists(path + ".tmp")
