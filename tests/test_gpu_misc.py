@@ -139,7 +139,10 @@ def test_training_resume_continues_the_same_trajectory(prec, tmp_path):
     assert max(abs(x - y) for x, y in zip(losses_a, losses_b + losses_c)) < tol, (losses_a, losses_b + losses_c)
     pa, pc = arena_of(m_a).flat, arena_of(m_c).flat
     assert (pa - pc).abs().mean().item() < (1e-5 if prec == "fp32" else 5e-4)
-    # control: same weights and moments, RNG streams NOT restored -> other dropout masks / eps
+    if prec != "fp32":
+        return
+    # control (fp32, where the tolerance is tight enough to see it): same weights and moments, RNG streams NOT
+    # restored -> other dropout masks / eps
     torch.manual_seed(777)
     random.seed(777)
     m_d = MeasureVAE(ds, encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
