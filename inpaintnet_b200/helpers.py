@@ -11,6 +11,9 @@ def to_cuda_variable(tensor):
 
 def to_cuda_variable_long(tensor):
     if torch.cuda.is_available():
+        if tensor.device.type == "cpu" and tensor.dtype != torch.int64 and tensor.is_pinned():
+            # pinned host batch (the loaders pin): upload the narrow type asynchronously, widen on the device
+            return tensor.cuda(non_blocking=True).long()
         return tensor.long().cuda()
     return tensor.long()
 

@@ -29,6 +29,53 @@ except Exception:  # pragma: no cover
         return x
 
 
+class LaggedReadback:
+    """Per-step results (loss, accuracy, NaN flag, token-range flag) travel device -> pinned host as an async copy
+    queued behind the step's kernels; the host reads step i-1's slot while step i is already running, so the
+    one device->host read per step the reference does (utils/trainer.py:154) no longer drains the GPU."""
+
+    def __init__(self, depth=4):
+        self.depth = depth
+        self.slots = None
+        self.events = []
+        self.pending = []      # slot indices in flight, oldest first
+        self.n = 0
+
+    def push(self, loss, accuracy, arena):
+        if self.slots is None:
+            pin = loss.is_cuda
+            self.slots = torch.zeros(self.depth, 4, dtype=torch.float32, pin_memory=pin)
+            self.events = [torch.cuda.Event() if pin else None for _ in range(self.depth)]
+        if len(self.pending) == self.depth:
+            raise RuntimeError("LaggedReadback: pop before pushing more than `depth` steps")
+        slot = self.n % self.depth
+        self.n += 1
+        acc = accuracy if accuracy is not None else loss.new_zeros(())
+        row = torch.stack((loss.detach().float().mean(), acc.detach().float().mean(), arena.nan_flag[0].float(),
+                           arena.range_flag[0].float()))
+        self.slots[slot].copy_(row, non_blocking=True)
+        if self.events[slot] is not None:
+            self.events[slot].record()
+        self.pending.append(slot)
+
+    def pop(self, keep=1):
+        """Yields (loss, accuracy) of every queued step but the newest `keep`; raises on a raised device flag."""
+        out = []
+        while len(self.pending) > keep:
+            slot = self.pending.pop(0)
+            if self.events[slot] is not None:
+                self.events[slot].synchronize()
+            loss, acc, nan_f, range_f = self.slots[slot].tolist()
+            if nan_f != 0:
+                print('Model parameters have become nan')
+                raise ValueError
+            if range_f != 0:
+                print("Invalid Values of Indices")
+                raise ValueError
+            out.append((loss, acc))
+        return out
+
+
 class Trainer(ABC):
     def __init__(self, dataset, model, lr=1e-4, early_stopping=False):
         self.dataset = dataset
@@ -127,23 +174,37 @@ class Trainer(ABC):
                     print("Early Stopping")
                     return
 
+    def run_batch(self, batch, epoch_num=None, train=True, readback=None):
+        """One step on a host batch from the loader: upload (async from pinned memory), forward, and for train=True
+        backward + gradient exchange + Adam.  With `readback` the results are queued for a lagged host read
+        (no sync here); without it they are returned as device tensors."""
+        batch_data = self.process_batch_data(batch)
+        self.zero_grad()
+        if train:
+            loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
+            loss.backward()
+            self.step()
+        else:
+            with torch.no_grad():
+                loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
+        if readback is not None:
+            readback.push(loss, accuracy, arena_of(self.model))
+        return loss, accuracy
+
     def loss_and_acc_on_epoch(self, data_loader, epoch_num=None, train=True):
+        """utils/trainer.py:126-163.  The per-step loss / accuracy / guard-flag read lags one step behind the
+        launches (LaggedReadback), so the NaN and token-range guards fire one step late but the GPU never idles."""
         mean_loss = 0
         mean_accuracy = 0
+        rb = LaggedReadback()
         for sample_id, batch in tqdm(enumerate(data_loader)):
-            batch_data = self.process_batch_data(batch)
-            self.zero_grad()
-            if train:
-                loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
-                loss.backward()
-                self.step()
-            else:
-                with torch.no_grad():
-                    loss, accuracy = self.loss_and_acc_for_batch(batch_data, epoch_num, train=train)
-            mean_loss += to_numpy(loss.mean())        # the one host sync of the step
-            if accuracy is not None:
-                mean_accuracy += to_numpy(accuracy)
-            self.check_device_flags()
+            self.run_batch(batch, epoch_num, train, readback=rb)
+            for loss, acc in rb.pop(keep=1):
+                mean_loss += loss
+                mean_accuracy += acc
+        for loss, acc in rb.pop(keep=0):
+            mean_loss += loss
+            mean_accuracy += acc
         mean_loss /= len(data_loader)
         mean_accuracy /= len(data_loader)
         return (mean_loss, mean_accuracy)
