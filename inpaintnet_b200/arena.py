@@ -118,6 +118,20 @@ class ParamArena:
     def wants_grad(self, name):
         return self.by_name[name].requires_grad
 
+    def trainable_range(self, prefixes):
+        """[lo, hi) element range of the gradient arena holding exactly the trainable parameters whose names start
+        with one of `prefixes`, or None when there are none or they are not contiguous (early gradient exchange)."""
+        prefixes = (prefixes,) if isinstance(prefixes, str) else tuple(prefixes)
+        sel = [n for n, p in zip(self.names, self.params) if p.requires_grad and n.startswith(prefixes)]
+        if not sel:
+            return None
+        lo = min(self.offset[n] for n in sel)
+        hi = max(self.offset[n] + self.by_name[n].numel() for n in sel)
+        for n, p in zip(self.names, self.params):
+            if p.requires_grad and n not in sel and lo <= self.offset[n] < hi:
+                return None
+        return lo, min(_round_up(hi, 4), self.n_trainable)
+
     def zero_grad(self):
         self.grad[: self.n_trainable].zero_()
         for n, p in zip(self.names, self.params):

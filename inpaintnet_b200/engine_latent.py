@@ -288,6 +288,7 @@ def latent_backward(arena, prec, saved, dweights, dz_out):
             bigru2_backward(arena, "generation_rnn.", prec, steps[i]["saved_gen"], dY1=(dY1.data_ptr(), 2 * Hg), dh_n=dh_n,
                             dh0=as_dst(dh0_i))
             dh0 = dh0_i
+    engine.grad_ready(arena, ("generation_rnn.", "generation_linear."))   # exchanged under the context GRUs' backward
     for k, (pfx, col0) in enumerate(saved["ctx"]):
         bigru2_backward(arena, pfx, prec, saved["saved_ctx"][k],
                         dh_n=[[(dh0[l, d].data_ptr() + 4 * col0, Hg) for d in range(2)] for l in range(2)])

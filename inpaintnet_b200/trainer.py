@@ -221,6 +221,8 @@ class Trainer(ABC):
             raise ValueError
 
     def zero_grad(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.grad_exchange()   # hook armed before the backward pass of this step
         self.optimizer.zero_grad()
 
     def step(self):
@@ -229,10 +231,17 @@ class Trainer(ABC):
         from .engine import SIDE
         SIDE.join()   # weight-gradient GEMMs deferred to the side stream (normally already joined by the autograd callback)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            a = arena_of(self.model)
-            allreduce_grads(a)
+            self.grad_exchange().finish(arena_of(self.model))   # buckets not already reduced under the backward pass
             scale = 1.0 / dist.get_world_size()
         self.optimizer.step(grad_scale=scale)
+
+    def grad_exchange(self):
+        """The overlapped gradient exchange of this trainer; installs the backward-pass hook on first use."""
+        from . import engine
+        if getattr(self, "_grad_exchange", None) is None:
+            self._grad_exchange = GradExchange()
+        engine.GRAD_READY = self._grad_exchange.ready
+        return self._grad_exchange
 
     @abstractmethod
     def loss_and_acc_for_batch(self, batch, epoch_num=None, train=True):
@@ -278,6 +287,55 @@ class Trainer(ABC):
     def mean_accuracy_alt(weights, targets):
         with torch.no_grad():
             return Fn.fused_ce_kl(weights.detach(), targets)[1]
+
+
+class GradExchange:
+    """Bucketed gradient all-reduce OVERLAPPED with the backward pass (one process per GPU, NCCL over NVLink).
+    The backward passes announce parameter groups whose gradients are complete (engine.grad_ready: the decoder
+    before the encoder backward starts, the generation GRU before the context GRUs); their buckets are reduced on
+    a communication stream while the remaining layers run.  finish() reduces whatever was not announced and makes
+    the current stream wait for every bucket.  All ranks run the same kernels in the same order (rank-shared
+    seeds), so the collectives are issued in the same order everywhere."""
+
+    def __init__(self, bucket_bytes=32 << 20):
+        self.bucket = max(1, bucket_bytes // 4)
+        self.comm = None
+        self.works = []
+        self.done = []          # [lo, hi) ranges already queued this step
+        self.n_early = 0        # buckets queued from inside the backward pass (diagnostics / tests)
+
+    def _queue(self, arena, lo, hi):
+        for a in range(lo, hi, self.bucket):
+            self.works.append(dist.all_reduce(arena.grad[a:min(hi, a + self.bucket)], op=dist.ReduceOp.SUM, async_op=True))
+
+    def ready(self, arena, prefixes, side_stream=None):
+        r = arena.trainable_range(prefixes)
+        if r is None or any(lo < r[1] and r[0] < hi for lo, hi in self.done):
+            return
+        if arena.grad.is_cuda:
+            if self.comm is None:
+                self.comm = torch.cuda.Stream()
+            self.comm.wait_stream(torch.cuda.current_stream())
+            if side_stream is not None:
+                self.comm.wait_stream(side_stream)
+            with torch.cuda.stream(self.comm):
+                n0 = len(self.works)
+                self._queue(arena, *r)
+        else:
+            n0 = len(self.works)
+            self._queue(arena, *r)
+        self.n_early += len(self.works) - n0
+        self.done.append(r)
+
+    def finish(self, arena):
+        pos = 0
+        for lo, hi in sorted(self.done) + [(arena.n_trainable, arena.n_trainable)]:
+            if pos < lo:
+                self._queue(arena, pos, lo)
+            pos = max(pos, hi)
+        for w in self.works:
+            w.wait()
+        self.works, self.done = [], []
 
 
 def allreduce_grads(arena, bucket_bytes=32 << 20):

@@ -39,6 +39,25 @@ def _worker(rank, world, port, q):
         exp = torch.arange(a.n_trainable, dtype=torch.float32) * sum(r + 1 for r in range(world))
         ok = torch.equal(a.grad[: a.n_trainable], exp) and bool((a.grad[a.n_trainable:] == 7.0 * (rank + 1)).all())
         ok = ok and m[0].weight.grad.data_ptr() == a.grad.data_ptr()
+        # overlapped exchange: a parameter group announced early + the rest at finish(), small buckets, two rounds
+        from inpaintnet_b200.trainer import GradExchange
+        m2 = torch.nn.ModuleDict(dict(enc=torch.nn.Linear(11, 13), dec=torch.nn.Linear(13, 7), frozen=torch.nn.Linear(7, 3)))
+        for p in m2["frozen"].parameters():
+            p.requires_grad = False
+        a2 = ParamArena(m2)
+        ex = GradExchange(bucket_bytes=64)
+        for rnd in range(2):
+            a2.zero_grad()
+            a2.grad[: a2.n_trainable] = torch.arange(a2.n_trainable, dtype=torch.float32) * (rank + 1 + rnd)
+            ex.ready(a2, "frozen.")                      # no trainable parameter: ignored
+            ex.ready(a2, "dec.")
+            ex.ready(a2, "dec.")                         # announced twice: reduced once
+            early = ex.n_early
+            ex.finish(a2)
+            exp2 = torch.arange(a2.n_trainable, dtype=torch.float32) * sum(r + 1 + rnd for r in range(world))
+            ok = ok and torch.equal(a2.grad[: a2.n_trainable], exp2) and early > 0 and not ex.done and not ex.works
+        lo, hi = a2.trainable_range("dec.")
+        ok = ok and (lo, hi) == (a2.offset["dec.weight"], a2.n_trainable) and a2.trainable_range(("enc.weight", "dec.bias")) is None
         # rank-shared seeds -> identical TF coins and splits on every rank
         coins = [random.random() < 0.5 for _ in range(8)]
         ds = SyntheticFolkDataset(num_notes=20)

@@ -1,5 +1,5 @@
 """Data-parallel parity on real GPUs (needs >= 2; skipped otherwise): two NCCL ranks, each with half of the
-batch, must end a training step with the same parameters as one process that saw the whole batch."""
+batch, must end two training steps (gradient buckets all-reduced under the backward pass) with the same parameters as one process that saw the whole batch."""
 import os
 import socket
 
@@ -55,7 +55,10 @@ def _worker(rank, world, port, q):
         per = B // world
         m, tr = _build(fx, f"cuda:{rank}")
         sl = slice(rank * per, (rank + 1) * per)
-        _step(m, tr, fx["tokens"][sl].cuda(), fx["eps"][sl])
+        for _ in range(2):
+            _step(m, tr, fx["tokens"][sl].cuda(), fx["eps"][sl])
+        # the decoder's gradient buckets must have been queued from inside the backward pass (overlap), both steps
+        assert tr._grad_exchange.n_early >= 2, tr._grad_exchange.n_early
         q.put((rank, {k: v.detach().cpu() for k, v in m.state_dict().items()}))
         dist.barrier()
     finally:
@@ -78,8 +81,9 @@ def test_two_rank_step_equals_full_batch_step():
     fx = torch.load(os.path.join(G, "mvae_h32.pt"), weights_only=False)
     B = fx["B"] // world * world
     m, tr = _build(fx, "cuda:0")
-    _step(m, tr, fx["tokens"][:B].cuda(), fx["eps"][:B])
+    for _ in range(2):
+        _step(m, tr, fx["tokens"][:B].cuda(), fx["eps"][:B])
     ref = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     for k in ref:
         assert torch.allclose(res[0][k], res[1][k], atol=0, rtol=0), k            # replicas stay identical
-        assert torch.allclose(res[0][k], ref[k], atol=3e-6, rtol=1e-4), k          # mean-of-means == global mean
+        assert torch.allclose(res[0][k], ref[k], atol=1e-5, rtol=2e-4), k          # mean-of-means == global mean
