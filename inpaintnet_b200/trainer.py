@@ -303,13 +303,14 @@ class GradExchange:
         self.works = []
         self.done = []          # [lo, hi) ranges already queued this step
         self.n_early = 0        # buckets queued from inside the backward pass (diagnostics / tests)
+        self.overlap = os.environ.get("IPN_DP_OVERLAP", "1") != "0"   # 0: everything is reduced at finish()
 
     def _queue(self, arena, lo, hi):
         for a in range(lo, hi, self.bucket):
             self.works.append(dist.all_reduce(arena.grad[a:min(hi, a + self.bucket)], op=dist.ReduceOp.SUM, async_op=True))
 
     def ready(self, arena, prefixes, side_stream=None):
-        r = arena.trainable_range(prefixes)
+        r = arena.trainable_range(prefixes) if self.overlap else None
         if r is None or any(lo < r[1] and r[0] < hi for lo, hi in self.done):
             return
         if arena.grad.is_cuda:
