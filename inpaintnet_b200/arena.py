@@ -176,13 +176,30 @@ class ParamArena:
             return False
         key = self.version_key()
         if key == self._shadow_key and self._shadow_items is not None:
+            self._await(getattr(self, "_shadow_ready", None))
             return False
         if self._shadow_items is None:
             self._shadow_table()
         items, n, max_rows, max_ld = self._shadow_items
         ops.pack_bf16(items.data_ptr(), n, max_rows, max_ld)
         self._shadow_key = key
+        self._shadow_ready = self._mark()
         return True
+
+    # caches filled on one stream and read on another (micro-batches pipelined on two streams): the reader waits
+    # for the event recorded behind the kernels that filled the cache
+    def _mark(self):
+        if self.flat.is_cuda:
+            s = torch.cuda.current_stream()
+            return s, s.record_event()
+        return None
+
+    @staticmethod
+    def _await(mark):
+        if mark is not None:
+            cur = torch.cuda.current_stream()
+            if cur != mark[0]:
+                cur.wait_event(mark[1])
 
     def w(self, prec, name, col0=0, cols=None):
         """(device pointer, leading dimension) of a 2-D weight block in the operand dtype of `prec`.
@@ -207,8 +224,10 @@ class ParamArena:
             self._derived = {}
             self._derived_key = vk
         if key not in self._derived:
-            self._derived[key] = builder()
-        return self._derived[key]
+            self._derived[key] = (builder(), self._mark())
+        else:
+            self._await(self._derived[key][1])
+        return self._derived[key][0]
 
     # ------------------------------------------------------------------ randomness
     def next_rng_offset(self, n_counters):

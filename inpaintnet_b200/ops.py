@@ -50,6 +50,7 @@ def ptr(t, elem_off=0):
 
 _gemm = L.Gemm()
 GEMM_MAX_CTAS = 0   # >0 while GEMMs are being issued on a side stream next to a persistent layer kernel
+GEMM_MAIN_MAX_CTAS = 0   # >0: grid cap of every other GEMM (micro-batches pipelined on two streams share the SMs)
 
 
 def gemm(core, in_dt, M, N, segs, out, out_dt, ld_out, bias=0, act=ACT_NONE, alpha=1.0, rowmap=None,
@@ -72,7 +73,7 @@ def gemm(core, in_dt, M, N, segs, out, out_dt, ld_out, bias=0, act=ACT_NONE, alp
         g.mul_src, g.mul_mode = None, MUL_NONE
     else:
         g.mul_src, g.mul_dt, g.ld_mul, g.mul_mode, g.mul_scale = mul
-    g.accumulate, g.split_k, g.max_ctas = accumulate, split_k, GEMM_MAX_CTAS
+    g.accumulate, g.split_k, g.max_ctas = accumulate, split_k, GEMM_MAX_CTAS or GEMM_MAIN_MAX_CTAS
     L.check(lib().ipn_gemm(C.byref(g), stream()))
 
 
