@@ -222,9 +222,45 @@ def test_pipelined_microbatches_match_single_stream_step(prec, B, H, mode):
             pytest.skip("argmax decode diverged between the two runs (bf16 tie)")   # deterministic kernels: not expected
         assert abs(l1 - l2) < (1e-5 if prec == "fp32" else 2e-3), (s, l1, l2)
         assert abs(a1 - a2) < 1e-6 + (0 if prec == "fp32" else 1e-3)
-        for k in g1:
-            scale = max(g1[k].abs().max().item(), 1e-8)
-            assert (g1[k] - g2[k]).abs().max().item() / scale < (2e-4 if prec == "fp32" else 3e-2), (s, k)
+        for k in g1:   # bf16: activations of a micro-batch are rounded like those of the full batch, sums differ in order
+            err = (g1[k] - g2[k]).norm().item() / max(g1[k].norm().item(), 1e-8)
+            assert err < (2e-4 if prec == "fp32" else 3e-2), (s, k, err)
         if s == 0:
             for k in p1:
                 assert (p1[k] - p2[k]).abs().mean().item() < (1e-6 if prec == "fp32" else 2e-4), (s, k)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_full_size_batch_against_oracle_on_row_subsets(prec):
+    """BASELINE.json configs[1] size (4096 measures, reference default hyper-parameters, V=64): measures are
+    independent, so rows taken from different 128-row tiles of the full-size run must match the CPU oracle run on
+    just those rows (logits / latents: 1e-3 relative in fp32 mode, 2e-2 in bf16 mode), teacher forced and argmax."""
+    V, H, Z, B = 64, 512, 256, 4096
+    fx = dict(V=V, H=H, Z=Z, seed=4321)
+    m, sd = build(fx, prec)
+    m.eval()
+    g = torch.Generator().manual_seed(17)
+    tokens = torch.randint(0, V, (B, 24), generator=g)
+    eps = torch.randn(B, Z, generator=g)
+    rows = torch.cat([torch.arange(a, a + 8) for a in (0, 120, 1021, 2048, 3333, 4088)])
+    tol = 1e-3 if prec == "fp32" else 2e-2
+    for mode in ("tf", "argmax"):
+        m.decoder.teacher_forcing_prob = 2.0 if mode == "tf" else -1.0
+        with torch.no_grad(), engine.inject_noise(eps=[eps]):
+            w, s, zd, _, z, _ = m(tokens.to(DEV), train=True)
+        w_ref, s_ref, mu_ref, ls_ref, _ = O.mvae_forward(sd, tokens[rows], eps[rows], teacher_forced=(mode == "tf"))
+        assert rel_err(zd.loc.cpu()[rows], mu_ref) < tol
+        assert rel_err(zd.log_std.cpu()[rows], ls_ref) < tol
+        if mode == "tf":
+            assert rel_err(w.cpu()[rows], w_ref) < tol
+        else:   # free-running decode: compare every row up to its first differing token (all of it in fp32 mode)
+            same = (s.cpu()[rows, 0] == s_ref[:, 0])
+            n_ok = same.long().cumprod(1).sum(1)               # ticks before the first differing argmax token
+            top2 = w_ref.topk(2, dim=2).values
+            strict = (top2[..., 0] - top2[..., 1]) > (1e-4 if prec == "fp32" else 5e-2)
+            for r in range(len(rows)):
+                k = int(n_ok[r])
+                if k < 24:
+                    assert not bool(strict[r, k]), (mode, int(rows[r]), k)   # only a near-tie may flip a token
+                k = min(k + 1, 24)   # the logits of the first differing tick still come from identical inputs
+                assert rel_err(w.cpu()[rows[r], :k], w_ref[r, :k]) < tol, (mode, int(rows[r]))
