@@ -184,6 +184,8 @@ typedef struct {
   int final_dir_dt;
   long long ld_final_dir;
   int P_blocked; /* P was produced by ipn_gru_inproj_blocked (persistent kernel only; table/pvec must be null) */
+  int table_rows; /* rows of `table` (0 = unknown).  Known and <= 128 with no other input-projection term: the
+                     persistent kernel's blocked P is gathered from a folded bf16 copy of the table (HBM write bound) */
 } IpnGruDir;
 
 typedef struct {

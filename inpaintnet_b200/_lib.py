@@ -35,7 +35,7 @@ class GruDir(C.Structure):
     _fields_ = [("w_hh", vp), ("b_hh", vp), ("P", vp), ("ldP", ll), ("P_bcast", i32), ("table", vp),
                 ("ld_table", ll), ("tok", vp), ("pvec", vp), ("hseq", vp), ("gates", vp), ("reverse", i32),
                 ("y_col0", i32), ("final_col0", i32), ("final_out_dir", vp), ("final_dir_dt", i32), ("ld_final_dir", ll),
-                ("P_blocked", i32)]
+                ("P_blocked", i32), ("table_rows", i32)]
 
 
 class GruInproj(C.Structure):

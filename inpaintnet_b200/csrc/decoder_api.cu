@@ -5,6 +5,7 @@ using namespace ipn;
 
 namespace ipn {
 bool gru_persist_fwd_shape_ok(const IpnGruLayer* L);
+long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L);
 }
 
 // the two per-tick GRU layer descriptors (row window = beat i of the batch, one step)
@@ -34,7 +35,11 @@ static bool tick_persist_ok(const IpnTickDecode* p) {
 
 extern "C" long long ipn_tick_decode_ws_bytes(const IpnTickDecode* p) {
   if (p == nullptr || !tick_persist_ok(p)) return 0;
-  return (long long)p->B * 3 * p->H * 2;
+  IpnGruLayer L0, L1;   // both per-tick layer calls share the workspace (stream ordered): the larger requirement
+  tick_layers(p, L0, L1);
+  L1.dir[0].P_blocked = 1;
+  const long long a = gru_persist_fwd_ws_bytes(&L0), b = gru_persist_fwd_ws_bytes(&L1);
+  return a > b ? a : b;
 }
 
 extern "C" int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream) {

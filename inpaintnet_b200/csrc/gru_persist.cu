@@ -72,6 +72,21 @@ __global__ void __launch_bounds__(256) gru_prep_p_kernel(PrepP p) {
   }
 }
 
+// Token-table input projection (encoder layer 0: P is a row of a <= 128-row table): nothing is materialised.  The
+// table is folded once per call (same arithmetic and rounding as gru_prep_p_kernel: bf16((table + b_hh) * 0.5) for
+// r,z and bf16(table) for n) and the layer kernel's epilogue gathers its rows by token id (L2-resident, 3H * 2 B per
+// row) -- for 98304 context measures that removes 14.5 GB of HBM writes and the same amount of reads per layer.
+__global__ void gru_fold_table_kernel(const float* table, long long ld_table, int rows, const float* b_hh, int H,
+                                      __nv_bfloat16* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 3 * H) return;
+  const int r = i / (3 * H), c = i - r * 3 * H;
+  float f = 0.f;
+  f += table[(long long)r * ld_table + c];
+  const float cst = c < 2 * H ? b_hh[c] : 0.f;
+  out[i] = __float2bfloat16_rn((f + cst) * (c < 2 * H ? 0.5f : 1.f));
+}
+
 // y[R, col0 + u] = keep[R, col0 + u] ? y * scale : 0   (inter-layer dropout applied after the layer kernel)
 __global__ void gru_mask_y_kernel(__nv_bfloat16* y, long long ld_y, const unsigned char* mask, long long ld_mask,
                                   int col0, int H, long long rows, float scale, int nrows, int Bt, int tt_min, int row0) {
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       uint32_t phase = 0;
       // the epilogue's input-projection tiles are pulled from HBM into L2 well ahead of their use
       auto prefetch_p = [&](int t, int c) {
-        if (t >= NS || (p.dbg & 16)) return;
+        if (t >= NS || (p.dbg & 16) || D.Pblk == nullptr) return;
         const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
         const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
         const int vpr = H >> 3;
@@ -321,8 +336,21 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     const long long te0 = clock64();
     const bool ldp = !(p.dbg & 1);
     // input projection, register double-buffered one chunk ahead (the tiles were prefetched into L2 earlier)
+    int tok_t = -1, tokv = 0;   // token-table mode: this row's token of step tok_t
     auto load_p = [&](uint4 (&dst)[3][2], int t, int c) {
       const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
+      if (D.ftab != nullptr) {   // gather the folded table row of this thread's token (L2 / L1 hits)
+        if (t != tok_t) {
+          tokv = __ldg(D.tok + (long long)tt * Bt + rbase + row);
+          tok_t = t;
+        }
+        const uint4* base = D.ftab + (long long)tokv * (3 * vpr) + c * 8 + sub * 2;
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) dst[g][v] = ldp ? __ldg(base + g * vpr + v) : make_uint4(0, 0, 0, 0);
+        return;
+      }
       const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
       const uint4* base = D.Pblk + (rt * 3 * vpr + c * 8 + sub * 2) * 128 + row;
 #pragma unroll
@@ -446,10 +474,20 @@ bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
   return true;
 }
 
+constexpr int GPF_FOLD_ROWS = 128;   // largest token table the gather path folds (vocabularies are 45-90 symbols)
+static bool dir_gathers_table(const IpnGruDir& D) {
+  static const int on = getenv("IPN_GPF_GATHER") ? atoi(getenv("IPN_GPF_GATHER")) : 1;
+  return on && D.table != nullptr && D.tok != nullptr && D.P == nullptr && D.pvec == nullptr && !D.P_blocked &&
+         D.table_rows > 0 && D.table_rows <= GPF_FOLD_ROWS;
+}
+
 long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L) {
   if (!gru_persist_fwd_shape_ok(L)) return 0;
-  long long per_dir = (long long)(L->s_end - L->s_begin) * L->nrows * 3 * L->H * 2;
-  return per_dir * L->ndir;
+  const long long per_dir = (long long)(L->s_end - L->s_begin) * L->nrows * 3 * L->H * 2;
+  long long total = 0;   // per direction: the folded token table, or the blocked P of this call's window, or nothing
+  for (int d = 0; d < L->ndir; ++d)
+    total += dir_gathers_table(L->dir[d]) ? GPF_FOLD_ROWS * 3LL * L->H * 2 : (L->dir[d].P_blocked ? 0 : per_dir);
+  return total > 16 ? total : 16;
 }
 
 int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStream_t stream) {
@@ -485,7 +523,17 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     o.gates = reinterpret_cast<uint4*>(D.gates);
     save = save || D.gates != nullptr;
     const int tt_min = D.reverse ? T - L->s_end : L->s_begin;   // earliest time index this call touches
-    if (D.P_blocked) {
+    if (dir_gathers_table(D)) {
+      __nv_bfloat16* ft = reinterpret_cast<__nv_bfloat16*>(wsp);
+      ProfScope prof("gru_fold_table", 0.0, (double)D.table_rows * 3 * H * 6, stream);
+      gru_fold_table_kernel<<<(D.table_rows * 3 * H + 255) / 256, 256, 0, stream>>>(D.table, D.ld_table, D.table_rows,
+                                                                                    D.b_hh, H, ft);
+      IPN_LAUNCH_CHECK();
+      o.ftab = reinterpret_cast<const uint4*>(ft);
+      o.tok = D.tok;
+      o.Pblk = nullptr;
+      wsp += GPF_FOLD_ROWS * 3LL * H * 2;
+    } else if (D.P_blocked) {
       o.Pblk = reinterpret_cast<const uint4*>(D.P);   // global blocked layout over all T*Bt rows
       o.p_t_stride = Bt / GP_ROWS;
       o.p_t0 = L->row0 / GP_ROWS;

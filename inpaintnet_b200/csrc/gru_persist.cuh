@@ -30,6 +30,8 @@ struct GruPersistFwdDir {
   alignas(64) CUtensorMap tmH;  // hseq [(T+1)*Bt, H], box 64 x 128 (loads and stores)
   alignas(64) CUtensorMap tmY;  // y [T*Bt, ld_y], box 64 x 128 (stores)
   const uint4* Pblk;            // blocked [T*Bt, 3, H] input projection, nullable
+  const uint4* ftab;            // token-table mode: folded bf16 table [rows, 3H]; P(t, row) = ftab[tok[t, row]] (Pblk null)
+  const int* tok;               // token ids [T*Bt], time-ordered rows
   uint4* gates;                 // blocked [T*Bt, 5, H], nullable
   const float* b_hh;
   const float* pvec;            // nullable

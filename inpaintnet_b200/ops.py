@@ -102,9 +102,9 @@ def gru_inproj_blocked(X, ldx, rows, K, w_ih, ldw, b_ih, b_hh, H, out):
 
 
 def gru_dir(w_hh, b_hh, hseq, gates=0, P=0, ldP=0, P_bcast=0, table=0, ld_table=0, tok=0, pvec=0, reverse=0,
-            y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0, P_blocked=0):
+            y_col0=0, final_col0=0, final_out=0, final_dt=F32, ld_final=0, P_blocked=0, table_rows=0):
     d = L.GruDir()
-    d.P_blocked = P_blocked
+    d.P_blocked, d.table_rows = P_blocked, table_rows
     d.final_out_dir, d.final_dir_dt, d.ld_final_dir = final_out or None, final_dt, ld_final
     d.w_hh, d.b_hh, d.P, d.ldP, d.P_bcast = w_hh, b_hh, P or None, ldP, P_bcast
     d.table, d.ld_table, d.tok, d.pvec = table or None, ld_table, tok or None, pvec or None

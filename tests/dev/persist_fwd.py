@@ -35,7 +35,7 @@ def run(H, B, T, ndir, src, use_mask, persistent, seed=0, reps=0):
         if src == "P":
             kw = dict(P=P[d].data_ptr(), ldP=3 * H)
         elif src == "table":
-            kw = dict(table=table[d].data_ptr(), ld_table=3 * H, tok=tok.data_ptr())
+            kw = dict(table=table[d].data_ptr(), ld_table=3 * H, tok=tok.data_ptr(), table_rows=V)
         elif src == "pvec":
             kw = dict(pvec=pvec[d].data_ptr())
         elif src == "bcast+table":

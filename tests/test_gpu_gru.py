@@ -171,3 +171,39 @@ def test_lstm_layer_fwd_bwd(prec_name, H, B, T):
     assert (gb.cpu() - Wr["b_ih"].grad).abs().max() <= a * max(1.0, Wr["b_ih"].grad.abs().max().item())
     dx_ref = xr.grad.transpose(0, 1).reshape(T * B, I)
     assert (dX.cpu() - dx_ref).abs().max() <= a * max(1.0, dx_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("H,B,T,V", [(512, 512, 7, 64), (128, 256, 5, 11), (64, 128, 3, 128), (320, 384, 4, 90)])
+def test_persistent_layer_token_table_gather_is_bit_exact(H, B, T, V):
+    """Encoder layer 0: the input projection is a row of a token table.  With table_rows given the blocked P of the
+    persistent kernel is gathered from a folded bf16 table (gru_gather_p_kernel); without it the generic relayout
+    kernel builds it.  Same arithmetic and rounding: the layer outputs must be identical bit for bit."""
+    from inpaintnet_b200 import ops
+    from inpaintnet_b200.ops import Precision
+    prec = Precision("bf16")
+    ndir = 2
+    g = torch.Generator().manual_seed(H + B)
+    s = 1.0 / H ** 0.5
+    whh = [((torch.rand(3 * H, H, generator=g) * 2 - 1) * s).to(DEV).bfloat16().contiguous() for _ in range(ndir)]
+    bhh = [((torch.rand(3 * H, generator=g) * 2 - 1) * s).to(DEV) for _ in range(ndir)]
+    table = torch.randn(ndir, V, 3 * H, generator=g).to(DEV)
+    tok = torch.randint(0, V, (T * B,), generator=g).int().to(DEV)
+    tok[:V] = torch.arange(V, dtype=torch.int32)          # every table row is used
+    h0 = (torch.randn(ndir, B, H, generator=g) * 0.5).to(DEV).bfloat16()
+
+    def run(rows):
+        hseq = torch.zeros(ndir, (T + 1) * B, H, dtype=torch.bfloat16, device=DEV)
+        hseq[0, :B] = h0[0]
+        hseq[1, T * B:] = h0[1]
+        y = torch.zeros(T * B, ndir * H, dtype=torch.bfloat16, device=DEV)
+        dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), reverse=d, y_col0=d * H,
+                            table=table[d].data_ptr(), ld_table=3 * H, tok=tok.data_ptr(), table_rows=rows) for d in range(ndir)]
+        assert ops.gru_layer_fwd(prec, T, B, H, dirs, y=y.data_ptr(), ld_y=ndir * H)   # True: the persistent kernel ran
+        torch.cuda.synchronize()
+        return y, hseq
+
+    y_ref, h_ref = run(0)
+    for _ in range(3):
+        y, h = run(V)
+        assert torch.equal(y, y_ref) and torch.equal(h, h_ref)
+    assert y_ref.float().abs().max().item() > 0.1
