@@ -189,6 +189,15 @@ def test_reference_train_inpaintnet_runs_unchanged_against_dropin(auto_reg, teac
                           log=False, auto_reg=auto_reg, teacher_forcing=teacher_forcing, early_stop=True, **_VAE_KW)
 
 
+def test_reference_train_inpaintnet_ablation_runs_unchanged_against_dropin():
+    """train_inpaintnet_ablation.py, unmodified (LatentRNNAblations, type='past')."""
+    _run_reference_script("train_measure_vae.py", batch_size=2, num_epochs=1, train=True, plot=False, log=False, lr=1e-4,
+                          **_VAE_KW)
+    _run_reference_script("train_inpaintnet_ablation.py", num_latent_rnn_layers=2, latent_rnn_hidden_size=32,
+                          latent_rnn_dropout_prob=0.5, batch_size=2, num_epochs=1, train=True, lr=1e-4, plot=False,
+                          log=False, auto_reg=True, teacher_forcing=True, early_stop=True, **_VAE_KW)
+
+
 @pytest.mark.parametrize("script", ["train_arnn_reg.py", "train_arnn_baseline.py"])
 def test_reference_train_arnn_runs_unchanged_against_dropin(script):
     """train_arnn_reg.py / train_arnn_baseline.py, unmodified: trainer epoch, then AnticipationRNNTester.test_model
