@@ -56,11 +56,31 @@ class LatentRNNTester(object):
         self._split.min_num_measures_target, self._split.max_num_measure_target = 2, 6
         self._split.measure_seq_len = 24
 
+    def split_score_stochastic(self, score_tensor, extra_outs=False, fix_num_target=None):
+        """latent_rnn_tester.py:359-414: as the trainer's split, but the past context may be as short as one
+        measure (low=1) and at least one future measure is kept."""
+        measures = LatentRNNTrainer.split_to_measures(score_tensor, self.measure_seq_len)
+        n = measures.size(1)
+        assert n == self.dataset.n_bars
+        if fix_num_target is None:
+            num_target = int(torch.randint(low=self._split.min_num_measures_target,
+                                           high=self._split.max_num_measure_target + 1, size=(1,)).item())
+        else:
+            num_target = fix_num_target
+        num_past = int(torch.randint(low=1, high=n - num_target - 1, size=(1,)).item())
+        num_future = n - num_past - num_target
+        past, future, target = LatentRNNTrainer.split_score(score_tensor=score_tensor, num_past=num_past,
+                                                            num_future=num_future, num_target=num_target,
+                                                            measure_seq_len=self.measure_seq_len)
+        if extra_outs:
+            return past, future, target, num_past, num_target
+        return past, future, target
+
     def test_model(self, batch_size=64):
         (_, _, gen_test) = self.dataset.data_loaders(batch_size=batch_size, split=(0.01, 0.01))
         mean_loss, mean_acc, n = 0, 0, 0
         for score_tensor, _ in gen_test:
-            past, future, target = self._split.split_score_stochastic(score_tensor)
+            past, future, target = self.split_score_stochastic(score_tensor)
             with torch.no_grad():
                 weights, _, _ = self.model(past_context=past, future_context=future, target=target,
                                            measures_to_generate=target.size(1), train=False)

@@ -198,6 +198,26 @@ def test_reference_train_inpaintnet_ablation_runs_unchanged_against_dropin():
                           log=False, auto_reg=True, teacher_forcing=True, early_stop=True, **_VAE_KW)
 
 
+def test_reference_test_reconstruction_runs_unchanged_against_dropin():
+    """test_reconstruction.py, unmodified: loads the four checkpoints the (equally unmodified) training scripts
+    wrote -- MeasureVAE, LatentRNN(auto_reg=False), ARNN, ARNN baseline -- and runs its three-model inpainting
+    comparison (LatentRNN.forward, forward_inpaint) over the held-out split."""
+    arnn_kw = dict(note_embedding_dim=10, metadata_embedding_dim=2, num_layers=2, lstm_hidden_size=32, dropout_lstm=0.2,
+                   input_dropout=0.2, linear_hidden_size=32)
+    lat_kw = dict(num_latent_rnn_layers=2, latent_rnn_hidden_size=32, latent_rnn_dropout_prob=0.5)
+    _run_reference_script("train_measure_vae.py", batch_size=2, num_epochs=1, train=True, plot=False, log=False, lr=1e-4,
+                          **_VAE_KW)
+    _run_reference_script("train_inpaintnet.py", batch_size=2, num_epochs=1, train=True, lr=1e-4, plot=False, log=False,
+                          auto_reg=False, teacher_forcing=True, early_stop=True, **lat_kw, **_VAE_KW)
+    for script in ("train_arnn_reg.py", "train_arnn_baseline.py"):
+        _run_reference_script(script, batch_size=2, num_epochs=1, train=True, log=False, lr=1e-4, plot=False,
+                              teacher_forcing=True, early_stop=True, **arnn_kw)
+    kw = dict(_VAE_KW)
+    kw.update(lat_kw)
+    kw.update({k: v for k, v in arnn_kw.items() if k not in kw})
+    _run_reference_script("test_reconstruction.py", batch_size=2, num_target=2, num_models=4, **kw)
+
+
 @pytest.mark.parametrize("script", ["train_arnn_reg.py", "train_arnn_baseline.py"])
 def test_reference_train_arnn_runs_unchanged_against_dropin(script):
     """train_arnn_reg.py / train_arnn_baseline.py, unmodified: trainer epoch, then AnticipationRNNTester.test_model
