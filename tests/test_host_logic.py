@@ -299,3 +299,40 @@ def test_training_state_round_trip(tmp_path):
     assert random.random() == want["py"] and torch.equal(torch.rand(3), want["t"])
     assert (tr2.early_stopper.counter, tr2.early_stopper.best_score) == (tr.early_stopper.counter, tr.early_stopper.best_score)
     assert not os.path.exists(path + ".tmp")
+
+
+def test_lagged_readback_orders_results_and_raises_on_guard_flags():
+    """trainer.LaggedReadback (CPU tensors here: no pinned memory / events): results come back in step order, the
+    newest `keep` stay queued, a raised NaN / token-range flag surfaces as the reference's ValueError."""
+    from inpaintnet_b200.trainer import LaggedReadback
+
+    class _Arena:
+        def __init__(self):
+            self.nan_flag = torch.zeros(1, dtype=torch.int32)
+            self.range_flag = torch.zeros(1, dtype=torch.int32)
+
+    a, rb = _Arena(), LaggedReadback(depth=3)
+    got = []
+    for i in range(7):
+        rb.push(torch.tensor(float(i)), torch.tensor(i / 10.0), a)
+        got += rb.pop(keep=1)
+        assert len(rb.pending) == 1
+    got += rb.pop(keep=0)
+    assert [round(l) for l, _ in got] == list(range(7))
+    assert all(abs(acc - i / 10.0) < 1e-6 for i, (_, acc) in enumerate(got))
+    rb.push(torch.tensor(1.0), None, a)            # accuracy may be absent
+    assert rb.pop(keep=0) == [(1.0, 0.0)]
+    for _ in range(3):
+        rb.push(torch.tensor(0.0), None, a)
+    with pytest.raises(RuntimeError):
+        rb.push(torch.tensor(0.0), None, a)        # ring full: the caller must pop
+    rb.pop(keep=0)
+    a.range_flag[0] = 1
+    rb.push(torch.tensor(0.0), None, a)
+    with pytest.raises(ValueError):
+        rb.pop(keep=0)
+    a.range_flag[0] = 0
+    a.nan_flag[0] = 1
+    rb.push(torch.tensor(0.0), None, a)
+    with pytest.raises(ValueError):
+        rb.pop(keep=0)
