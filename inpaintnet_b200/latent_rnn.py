@@ -123,12 +123,6 @@ class LatentRNN(Model):
                                                   tgt, teacher_forcing)
         return weights, samples, gen_z
 
-    def save(self):
-        save_dir = os.path.dirname(self.filepath)
-        os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.state_dict(), self.filepath)
-        print(f'Model {self.__repr__()} saved')
-
     def xavier_initialization(self):
         for mod in (self.context_rnn_past, self.context_rnn_future, self.generation_rnn, self.generation_linear):
             for name, param in mod.named_parameters():

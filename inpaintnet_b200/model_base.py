@@ -1,5 +1,8 @@
-"""reference: utils/model.py:5-53 -- save / save_checkpoint / load = torch.save(state_dict) at `filepath`.
-The state_dict layout (names, shapes, fp32) is the reference's, so checkpoints are interchangeable."""
+"""Checkpoint plumbing shared by the models.  API of the reference's utils/model.py:5-53 (`save`, `save_checkpoint`,
+`load(cpu=False)`, the `filepath` attribute): a checkpoint is `torch.save(state_dict)` at `filepath` (per-epoch copies
+at `filepath_<epoch>`), and the state_dict layout (names, shapes, fp32) is the reference's, so files written by
+either implementation load in the other.  Optimiser / RNG state for a true resume lives in
+`Trainer.save_training_state`, next to this file."""
 import os
 
 import torch
@@ -13,20 +16,25 @@ class Model(torch.nn.Module):
     def forward(self):
         pass
 
+    def _write_state(self, path):
+        folder = os.path.dirname(path)
+        if folder:
+            os.makedirs(folder, exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save(self.state_dict(), tmp)
+        os.replace(tmp, path)      # never leave a truncated checkpoint behind
+
     def save(self):
-        save_dir = os.path.dirname(self.filepath)
-        if not os.path.exists(save_dir):
-            os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.state_dict(), self.filepath)
+        self._write_state(self.filepath)
         print(f'Model {self.__repr__()} saved')
 
     def save_checkpoint(self, epoch_num):
-        torch.save(self.state_dict(), self.filepath + '_' + str(epoch_num))
+        self._write_state(f'{self.filepath}_{epoch_num}')
         print(f'Model checkpoint {self.__repr__()} saved for epoch')
 
     def load(self, cpu=False):
-        if cpu:
-            self.load_state_dict(torch.load(self.filepath, map_location=lambda storage, loc: storage))
-        else:
-            self.load_state_dict(torch.load(self.filepath))
+        # parameters are copied INTO the arena views, so the target device is the model's own either way;
+        # `cpu=True` (reference: map_location to host storage) only decides where the file is staged
+        state = torch.load(self.filepath, map_location="cpu" if cpu else None)
+        self.load_state_dict(state)
         print(f'Model {self.__repr__()} loaded')
