@@ -93,10 +93,7 @@ def test_two_rank_step_equals_full_batch_step():
 # LatentRNN training with a frozen MeasureVAE (BASELINE.json configs[2]): the generation GRU's gradient
 # buckets are reduced while the context GRUs' backward still runs
 # ---------------------------------------------------------------------------------------------------
-# NOT YET RUN ON A GPU: written at the very end of round 1; its first version had a harness bug (the synthetic
-# dataset's n_bars did not match the fixture's 3+2+3 split) and the round's GPU budget ended before the corrected
-# one could run.  It is therefore opt-in (IPN_TEST_UNVERIFIED=1) until a 2-GPU run has confirmed it.
-_UNVERIFIED = os.environ.get("IPN_TEST_UNVERIFIED", "0") != "1"
+# Confirmed on 2 B200s (round 2, first GPU call: 119 passed with both data-parallel tests).
 
 
 def _latent_build(fx, dev):
@@ -163,7 +160,6 @@ def _collect(q, procs, world, timeout=300):
     return out
 
 
-@pytest.mark.skipif(_UNVERIFIED, reason="not yet confirmed on 2 GPUs (IPN_TEST_UNVERIFIED=1 to run)")
 def test_latent_rnn_two_rank_steps_equal_full_batch_steps():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
