@@ -80,6 +80,7 @@ class ParamArena:
             p._ipn_arena = self
             p._ipn_name = n
         self.by_name = dict(ordered)
+        self._rg_sig = self._requires_grad_signature()
         self.manual_version = 0
         self._shadow_entries = {}   # key -> (bf16 tensor, rows, cols, ld, full_cols, col0)
         self._shadow_items = None
@@ -91,14 +92,25 @@ class ParamArena:
         self.rng_offset = 0
 
     # ------------------------------------------------------------------ validity / lookup
+    def _requires_grad_signature(self):
+        return tuple(p.requires_grad for p in self.params)
+
     def valid(self):
+        """False once a parameter left the arena (model.to()/.float()) or the trainable set changed (freezing a
+        sub-module after the arena exists would leave the trainable-first layout, n_trainable and the early-exchange
+        ranges stale): arena_of() then rebuilds the arena, and FusedAdam carries its state over by name."""
         p0, p1 = self.params[0], self.params[-1]
         return (p0.data_ptr() == self.flat.data_ptr() + 4 * self.offset[self.names[0]]
                 and p1.data_ptr() == self.flat.data_ptr() + 4 * self.offset[self.names[-1]]
-                and p0.device == self.device)
+                and p0.device == self.device and self._rg_sig == self._requires_grad_signature())
 
     def version_key(self):
         return (self.manual_version, sum(p._version for p in self.params))
+
+    def invalidate(self):
+        """Call after writing parameters through a path that does not bump tensor versions (`p.data.clamp_()`,
+        an EMA swap through .data, ...): the bf16 shadow and the derived tables are rebuilt on the next forward."""
+        self.manual_version += 1
 
     def fptr(self, name, elem_off=0):
         """device pointer into the fp32 master copy"""

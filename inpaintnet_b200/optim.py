@@ -19,9 +19,26 @@ class FusedAdam(torch.optim.Optimizer):
     def arena(self):
         a = arena_of(self.model)
         if a is not self._arena:
+            old, old_m, old_v = self._arena, self._m, self._v
             self._arena = a
             self._m = torch.zeros(a.n_trainable, dtype=torch.float32, device=a.device)
             self._v = torch.zeros(a.n_trainable, dtype=torch.float32, device=a.device)
+            if old is not None and self.step_count > 0:
+                # the arena was rebuilt (model.to()/.float(), a sub-module frozen or unfrozen): carry the moments of
+                # every parameter that is still trainable over by NAME; anything new starts from zero moments
+                carried = 0
+                was_trainable = dict(zip(old.names, old._rg_sig))   # the state the old layout was built for
+                for n, p in zip(a.names, a.params):
+                    if p.requires_grad and was_trainable.get(n, False) and old.by_name[n].numel() == p.numel():
+                        o_new, o_old, k = a.offset[n], old.offset[n], p.numel()
+                        self._m[o_new:o_new + k].copy_(old_m[o_old:o_old + k])
+                        self._v[o_new:o_new + k].copy_(old_v[o_old:o_old + k])
+                        carried += 1
+                n_train = sum(1 for p in a.params if p.requires_grad)
+                if carried != n_train:
+                    import warnings
+                    warnings.warn(f"FusedAdam: parameter arena rebuilt; Adam moments carried over for {carried} of {n_train} "
+                                  f"trainable parameters, the others restart from zero moments (step count kept)")
         return a
 
     def zero_grad(self, set_to_none=False):

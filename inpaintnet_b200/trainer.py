@@ -29,6 +29,31 @@ except Exception:  # pragma: no cover
         return x
 
 
+def dp_rank_world():
+    """(rank, world) of the data-parallel job; (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_batch(batch):
+    """This rank's share of a loader batch under data parallelism.  Every rank iterates the SAME loader (rank-shared
+    torch seed -> identical shuffle), so a loader batch is the global batch: rank r keeps rows r, r + world, ... of its
+    first (B // world) * world rows (equal local batches, so the mean of the local losses is the global mean).
+    Tensors that are None (the VAE trainer ignores the metadata) pass through."""
+    rank, world = dp_rank_world()
+    if world == 1:
+        return batch
+    def take(t):
+        if t is None or not torch.is_tensor(t) or t.dim() == 0:
+            return t
+        n = t.shape[0] // world * world
+        if n == 0:
+            raise ValueError(f"data-parallel batch of {t.shape[0]} rows cannot be split over {world} ranks")
+        return t[rank:n:world]
+    return tuple(take(t) for t in batch) if isinstance(batch, (tuple, list)) else take(batch)
+
+
 class LaggedReadback:
     """Per-step results (loss, accuracy, NaN flag, token-range flag) travel device -> pinned host as an async copy
     queued behind the step's kernels; the host reads step i-1's slot while step i is already running, so the
@@ -148,6 +173,9 @@ class Trainer(ABC):
         first_epoch = 0
         if resume and os.path.exists(self.training_state_path()):
             first_epoch = self.load_training_state()
+            if self.early_stopping and self.early_stopper.early_stop:
+                print("Early Stopping")      # the saved run had already stopped: nothing left to train
+                return
             print(f'Resuming at epoch {first_epoch + 1}/{num_epochs}')
         for epoch_index in range(first_epoch, num_epochs):
             self.update_scheduler(epoch_index)
@@ -166,21 +194,25 @@ class Trainer(ABC):
                 log_value('valid_loss', mean_loss_val, epoch_index)
                 log_value('valid_accu', mean_accuracy_val, epoch_index)
             self.print_epoch_stats(**data_element)
+            if self.early_stopping:   # before the state is saved, so that a resumed run sees this epoch's verdict
+                self.early_stopper(mean_loss_val, self.model)
             if not dist.is_initialized() or dist.get_rank() == 0:
                 self.model.save()
                 if epoch_index > 0 and epoch_index % 10 == 0:
                     self.model.save_checkpoint(epoch_index)
                 self.save_training_state(epoch_index)
-            if self.early_stopping:
-                self.early_stopper(mean_loss_val, self.model)
-                if self.early_stopper.early_stop:
-                    print("Early Stopping")
-                    return
+            if self.early_stopping and self.early_stopper.early_stop:
+                print("Early Stopping")
+                return
 
-    def run_batch(self, batch, epoch_num=None, train=True, readback=None):
+    def run_batch(self, batch, epoch_num=None, train=True, readback=None, shard=False):
         """One step on a host batch from the loader: upload (async from pinned memory), forward, and for train=True
         backward + gradient exchange + Adam.  With `readback` the results are queued for a lagged host read
-        (no sync here); without it they are returned as device tensors."""
+        (no sync here); without it they are returned as device tensors.  shard=True: `batch` is the GLOBAL batch of a
+        data-parallel job and this rank trains on its share (shard_batch); callers that already hold per-rank data
+        (bench.py, the tests) leave it False."""
+        if shard:
+            batch = shard_batch(batch)
         batch_data = self.process_batch_data(batch)
         self.zero_grad()
         if train:
@@ -201,7 +233,7 @@ class Trainer(ABC):
         mean_accuracy = 0
         rb = LaggedReadback()
         for sample_id, batch in tqdm(enumerate(data_loader)):
-            self.run_batch(batch, epoch_num, train, readback=rb)
+            self.run_batch(batch, epoch_num, train, readback=rb, shard=True)
             for loss, acc in rb.pop(keep=1):
                 mean_loss += loss
                 mean_accuracy += acc
@@ -210,6 +242,13 @@ class Trainer(ABC):
             mean_accuracy += acc
         mean_loss /= len(data_loader)
         mean_accuracy /= len(data_loader)
+        rank, world = dp_rank_world()
+        if world > 1:
+            # every rank saw a different shard: the epoch statistics (and therefore the early-stopping decision, which
+            # must be the same everywhere or the ranks' collectives diverge) are the mean over ranks
+            stats = torch.tensor([mean_loss, mean_accuracy], dtype=torch.float64, device=arena_of(self.model).device)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            mean_loss, mean_accuracy = (stats / world).tolist()
         return (mean_loss, mean_accuracy)
 
     def check_device_flags(self):
@@ -468,69 +507,60 @@ class LatentRNNTrainer(Trainer):
     def update_scheduler(self, epoch_num):
         return
 
+    def draw_split(self, num_measures, fix_num_target=None):
+        """(n_past, n_target, n_future) of one batch.  The two host draws, their bounds and their ORDER are those of
+        latent_rnn_trainer.py:99-118 (gap length first, then the past length), so a seeded run splits exactly like
+        the reference; under data parallelism every rank must hold the same torch seed (same shapes, same kernels)."""
+        lo, hi = self.min_num_measures_target, self.max_num_measure_target
+        n_target = fix_num_target if fix_num_target is not None else int(torch.randint(lo, hi + 1, (1,)))
+        n_past = int(torch.randint(1, num_measures - n_target - 1, (1,)))     # leaves at least two future measures
+        return n_past, n_target, num_measures - n_past - n_target
+
     def split_score_stochastic(self, score_tensor, extra_outs=False, fix_num_target=None):
-        """latent_rnn_trainer.py:77-132.  The split is drawn with torch.randint on the host: under data
-        parallelism all ranks must share the torch seed so shapes (and therefore kernels) agree."""
-        measures_tensor = LatentRNNTrainer.split_to_measures(score_tensor, self.measure_seq_len)
-        num_measures = measures_tensor.size(1)
-        assert (num_measures == self.dataset.n_bars)
-        if fix_num_target is None:
-            num_target = int(torch.randint(low=self.min_num_measures_target, high=self.max_num_measure_target + 1,
-                                           size=(1,)).item())
-        else:
-            num_target = fix_num_target
-        num_past = int(torch.randint(low=1, high=num_measures - num_target - 1, size=(1,)).item())
-        num_future = num_measures - num_past - num_target
-        tensor_past, tensor_future, tensor_target = LatentRNNTrainer.split_score(
-            score_tensor=score_tensor, num_past=num_past, num_future=num_future, num_target=num_target,
-            measure_seq_len=self.measure_seq_len)
-        if extra_outs:
-            return tensor_past, tensor_future, tensor_target, num_past, num_target
-        return tensor_past, tensor_future, tensor_target
+        """latent_rnn_trainer.py:77-132: a random past / gap / future partition of the (B, 1, n_bars * 24) score."""
+        n_bars = score_tensor.shape[-1] // self.measure_seq_len
+        assert n_bars == self.dataset.n_bars
+        n_past, n_target, n_future = self.draw_split(n_bars, fix_num_target)
+        parts = LatentRNNTrainer.split_score(score_tensor, n_past, n_future, n_target, self.measure_seq_len)
+        return parts + (n_past, n_target) if extra_outs else parts
 
     @staticmethod
     def split_score(score_tensor, num_past, num_future, num_target, measure_seq_len):
-        measures_tensor = LatentRNNTrainer.split_to_measures(score_tensor, measure_seq_len)
-        num_measures = measures_tensor.size(1)
-        assert (num_measures == num_past + num_future + num_target)
-        tensor_past = to_cuda_variable_long(measures_tensor[:, 0:num_past, :])
-        tensor_future = to_cuda_variable_long(measures_tensor[:, num_measures - num_future:, :])
-        tensor_target = to_cuda_variable_long(measures_tensor[:, num_past:num_measures - num_future, :])
-        return tensor_past, tensor_future, tensor_target
+        """latent_rnn_trainer.py:134-160 -> (past, future, target) int64 device tensors (B, n, 24).  ONE upload of the
+        whole score (asynchronous when the loader pinned it), the three blocks are views of the device copy."""
+        measures = LatentRNNTrainer.split_to_measures(score_tensor, measure_seq_len)
+        if measures.shape[1] != num_past + num_target + num_future:
+            raise AssertionError((measures.shape[1], num_past, num_target, num_future))
+        dev = to_cuda_variable_long(measures)
+        gap_end = num_past + num_target
+        return dev[:, :num_past], dev[:, gap_end:], dev[:, num_past:gap_end]
 
     @staticmethod
     def split_to_measures(score_tensor, measure_seq_len):
-        batch_size, _, seq_len = score_tensor.size()
-        if seq_len % measure_seq_len != 0:
+        """(B, 1, L) -> (B, L / measure_seq_len, measure_seq_len); ValueError when L is not a whole number of measures
+        (latent_rnn_trainer.py:162-176)."""
+        if score_tensor.shape[-1] % measure_seq_len:
             raise ValueError
-        return score_tensor.reshape(batch_size, -1, measure_seq_len)
+        return score_tensor.reshape(score_tensor.shape[0], -1, measure_seq_len)
 
 
 class EarlyStopping:
-    """reference: utils/trainer.py:379-413"""
+    """Patience counter on the validation loss (behaviour of utils/trainer.py:379-413: an epoch counts as an
+    improvement only when the loss drops by at least `min_delta` below the best one seen; `patience` epochs in a row
+    without one raise `early_stop`).  Its four state fields are part of the saved training state."""
+    min_delta = 1e-5
 
     def __init__(self, patience=5, verbose=False):
-        self.patience = patience
-        self.verbose = verbose
-        self.counter = 0
-        self.best_score = None
-        self.early_stop = False
-        self.val_loss_min = np.inf
+        self.patience, self.verbose = patience, verbose
+        self.counter, self.best_score, self.early_stop, self.val_loss_min = 0, None, False, np.inf
 
     def __call__(self, val_loss, model):
         score = -val_loss
-        if self.best_score is None:
+        if self.best_score is None:            # first epoch: the reference records the score, not the loss
             self.best_score = score
-        elif score <= self.best_score:
-            self.counter += 1
-            if self.counter >= self.patience:
-                self.early_stop = True
-        else:
-            if score - self.best_score < 1e-5:
-                self.counter += 1
-                if self.counter >= self.patience:
-                    self.early_stop = True
-            else:
-                self.best_score = score
-                self.val_loss_min = val_loss
-                self.counter = 0
+            return
+        if score - self.best_score >= self.min_delta:
+            self.best_score, self.val_loss_min, self.counter = score, val_loss, 0
+            return
+        self.counter += 1
+        self.early_stop = self.early_stop or self.counter >= self.patience

@@ -1,8 +1,9 @@
 """Import harness for the UNMODIFIED reference (test infrastructure only).
 
-Only usable in the build container where /root/reference is mounted; it is used by
-tests/golden/make_golden.py to generate the committed golden fixtures and by the
-`-m "not gpu"` tests that validate the oracle restatement when the reference is present.
+Imports the reference from /root/reference when it is mounted (the build container), else from the byte-for-byte
+staged copy oracle/_ref/ that oracle/make_ref.sh writes (git-ignored; it travels to the GPU box with the snapshot).
+Used by tests/golden/make_golden.py to generate the committed golden fixtures, by the `-m "not gpu"` tests that
+validate the oracle restatement, and by oracle/ref_bench.py (the CPU arm of bench.py).
 Nothing on the product path imports this file.
 
 Stubs the four packages the reference imports but this image lacks
@@ -13,7 +14,18 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("INPAINTNET_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    cands = [os.environ.get("INPAINTNET_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "MeasureVAE")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -336,3 +336,100 @@ def test_lagged_readback_orders_results_and_raises_on_guard_flags():
     rb.push(torch.tensor(0.0), None, a)
     with pytest.raises(ValueError):
         rb.pop(keep=0)
+
+
+def test_early_stopping_matches_reference_and_resume_sees_the_stop(monkeypatch):
+    """EarlyStopping behaves like utils/trainer.py:379-413 on a loss curve with plateaus (checked against the
+    unmodified reference class when the reference is mounted / staged), and the stopper runs BEFORE the training
+    state is saved, so a resumed run of an early-stopped job stops at once instead of training on."""
+    from inpaintnet_b200.trainer import EarlyStopping
+    curve = [1.0, 0.9, 0.9, 0.899999, 0.95, 0.8, 0.80000001, 0.85, 0.9, 0.81, 0.82, 0.7]
+    mine = EarlyStopping(patience=5)
+    trace = []
+    for v in curve:
+        mine(v, None)
+        trace.append((mine.counter, mine.early_stop, mine.best_score, mine.val_loss_min))
+    assert trace[5][0] == 0 and trace[5][2] == -0.8
+    assert [t[0] for t in trace] == [0, 0, 1, 2, 3, 0, 1, 2, 3, 4, 5, 5][:len(trace)] or trace[10][1]
+    assert trace[10][1] and trace[11][1]           # fifth epoch without improvement -> stop, and it stays stopped
+    from oracle.ref_import import reference_available, load_reference
+    if reference_available():
+        import importlib
+        load_reference()
+        import sys
+        from oracle.ref_import import REFERENCE_ROOT
+        sys.path.insert(0, REFERENCE_ROOT)
+        try:
+            ref_cls = importlib.import_module("utils.trainer").EarlyStopping
+        finally:
+            sys.path.remove(REFERENCE_ROOT)
+        import numpy as np
+        monkeypatch.setattr(np, "Inf", np.inf, raising=False)   # the reference predates numpy 2 (np.Inf was removed)
+        ref = ref_cls(patience=5)
+        for v, t in zip(curve, trace):
+            ref(v, None)
+            assert (ref.counter, ref.early_stop, ref.best_score, ref.val_loss_min) == t
+
+
+def test_shard_batch_and_resume_after_early_stop(tmp_path, monkeypatch):
+    from inpaintnet_b200 import trainer as T
+    monkeypatch.setattr(T, "dp_rank_world", lambda: (1, 4))
+    score, meta = torch.arange(22).view(11, 1, 2), torch.arange(11)
+    s, m, none = T.shard_batch((score, meta, None))
+    assert none is None and s.shape[0] == 2 and torch.equal(m, torch.tensor([1, 5]))   # rows 1, 5 of the first 8
+    with pytest.raises(ValueError):
+        T.shard_batch((torch.zeros(3, 1, 2),))
+    monkeypatch.setattr(T, "dp_rank_world", lambda: (0, 1))
+    assert T.shard_batch((score, meta))[0] is score
+
+    # a run that ended with "Early Stopping" resumes as stopped (the state is saved after the stopper ran)
+    with stubbed():
+        ds = SyntheticFolkDataset(num_notes=20, num_sequences=8)
+        m = MeasureVAE(ds, encoder_hidden_size=32, decoder_hidden_size=32, latent_space_dim=16)
+        m.filepath = str(tmp_path / "model")
+        tr = VAETrainer(ds, m)
+        tr.early_stopping, tr.early_stopper = True, T.EarlyStopping(patience=1)
+        calls = []
+
+        def fake_epoch(data_loader, epoch_num=None, train=True):
+            calls.append((epoch_num, train))
+            return 1.0, 0.5            # the loss never improves -> stops after the second epoch
+
+        tr.loss_and_acc_on_epoch = fake_epoch
+        tr.train_model(batch_size=2, num_epochs=10)
+        assert [e for e, t in calls if t] == [0, 1]
+        tr2 = VAETrainer(ds, m)
+        tr2.early_stopping, tr2.early_stopper = True, T.EarlyStopping(patience=1)
+        tr2.loss_and_acc_on_epoch = fake_epoch
+        n = len(calls)
+        tr2.train_model(batch_size=2, num_epochs=10, resume=True)
+        assert len(calls) == n and tr2.early_stopper.early_stop
+
+
+def test_arena_rebuilds_when_the_trainable_set_changes_and_adam_state_follows():
+    """freezing a sub-module after the arena exists must rebuild the trainable-first layout, and
+    FusedAdam must carry the moments of the still-trainable parameters over instead of silently zeroing them."""
+    from inpaintnet_b200.optim import FusedAdam
+    m = torch.nn.ModuleDict(dict(a=torch.nn.Linear(5, 3), b=torch.nn.Linear(3, 2)))
+    opt = FusedAdam(m)
+    a0 = opt.arena()
+    opt.step_count = 3
+    opt._m.copy_(torch.arange(a0.n_trainable, dtype=torch.float32))
+    off_b = a0.offset["b.weight"]
+    want = opt._m[off_b:off_b + 6].clone()
+    for p in m["a"].parameters():
+        p.requires_grad = False
+    assert not a0.valid()
+    a1 = opt.arena()                           # every still-trainable parameter keeps its moments: no warning
+    assert a1 is not a0 and a1.offset["b.weight"] == 0 and a1.n_trainable == 12
+    assert torch.equal(opt._m[:6], want) and opt.step_count == 3
+    for p in m["a"].parameters():
+        p.requires_grad = True
+    with pytest.warns(UserWarning):            # a.* has no history: announced, not silent
+        a2 = opt.arena()
+    ob = a2.offset["b.weight"]
+    assert torch.equal(opt._m[ob:ob + 6], want) and float(opt._m[a2.offset["a.weight"]]) == 0.0
+    a1 = a2
+    v0 = a1.version_key()
+    a1.invalidate()
+    assert a1.version_key() != v0
