@@ -243,12 +243,14 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=1e-4, b1
 
 def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, num_layers=2,
                        ctx_keep_masks=None, gen_keep_masks=None, dropout_p=0.0, vae_dropout=None,
-                       vae_dropout_p=0.0, only=None):
+                       vae_dropout_p=0.0, only=None, fed_tokens=None):
     """Non-autoregressive LatentRNN (auto_reg=False: what the evaluation scripts load,
     test_reconstruction.py:141).  past (B,np,24), future (B,nf,24) int64.
     eps_* (B,n,Z): injected rsample noise (latent_rnn.py:172 samples even in eval).
     Returns weights (B,n_gen,24,V), samples (B,1,24*n_gen), z_out (B,n_gen,Z).
     The target-encode of latent_rnn.py:133 does not influence any output in this mode.
+    fed_tokens (B,n_gen,24): test hook -- decode with THESE tokens fed back instead of the oracle's own argmax (no
+    gradient flows through the argmax, so this is the same function of the parameters along a given token path).
     only="past"/"future": LatentRNNAblations (latent_rnn_ablations.py:143-146), one context seeds the generation GRU."""
     B = past.shape[0]
     vp = "vae_model."
@@ -271,7 +273,10 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
                    sd["generation_linear.bias"]).view(B, n_gen, -1)           # latent_rnn.py:232-233
     ws, ss = [], []
     for i in range(n_gen):                                                     # latent_rnn.py:237-240
-        w, s = decoder_forward(sd, z_out[:, i], None, False, 2, prefix=vp + "decoder.")
+        if fed_tokens is None:
+            w, s = decoder_forward(sd, z_out[:, i], None, False, 2, prefix=vp + "decoder.")
+        else:
+            w, s = decoder_forward(sd, z_out[:, i], fed_tokens[:, i], True, 2, prefix=vp + "decoder.")
         ws.append(w)
         ss.append(s)
     return torch.stack(ws, 1), torch.cat(ss, 2), z_out
