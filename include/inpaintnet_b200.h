@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IPN_ABI_VERSION 2
+#define IPN_ABI_VERSION 3
 
 /* status codes */
 #define IPN_OK 0
@@ -145,6 +145,29 @@ typedef struct {
   void* out;
 } IpnGruInproj;
 int ipn_gru_inproj_blocked(const IpnGruInproj* p, void* stream);
+
+/* The same for an LSTM layer (4 gates [i; f; g; o]) and for an input that is the concatenation of up to two matrices
+ * (AnticipationRNN generation stack: [shifted note embedding | constraint output], arnn_model.py:375):
+ *   out = blocked bf16 [rows, 4, H] of   i, f, o: 0.5 * (X W_ih^T [+ X2 W_ih2^T] + b_ih + b_hh)     g: the same without the 0.5
+ * (the sigmoid gates are evaluated as 0.5 tanh(0.5 x) + 0.5).  Pass the result as IpnLstmLayer.P with P_blocked = 1. */
+typedef struct {
+  const void* X; /* [rows, K] bf16, row stride ldx */
+  long long ldx;
+  int K;
+  const void* w_ih; /* [4H, K] bf16, row stride ldw */
+  long long ldw;
+  const void* X2;   /* optional second segment [rows, K2] */
+  long long ldx2;
+  int K2;
+  const void* w_ih2; /* [4H, K2] */
+  long long ldw2;
+  long long rows;
+  const float* b_ih;
+  const float* b_hh;
+  int H;
+  void* out;
+} IpnLstmInproj;
+int ipn_lstm_inproj_blocked(const IpnLstmInproj* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GRU layer (all directions of ONE layer), forward.  replaces torch.nn.GRU.forward:
@@ -287,8 +310,19 @@ typedef struct {
   const float* table; /* optional [*, 4H] rows added to the input projection, selected by *tok_scalar (same row for */
   long long ld_table; /* the whole batch: AnticipationRNN no-teacher-forcing feedback, arnn_model.py:252-256)    */
   const int* tok_scalar;
+  int P_blocked; /* P was produced by ipn_lstm_inproj_blocked: the steps [s_begin, s_end) run as ONE persistent cluster
+                    kernel (needs ipn_lstm_persist_eligible; table must be null).  W_hh stays resident in the shared
+                    memory of a thread-block cluster (one 64-unit gate-column slice per CTA), h_t is exchanged through
+                    distributed shared memory once per step.  `gates` then has ipn_lstm_gates_cols(H) columns in a
+                    layout private to the fwd/bwd pair (i, f, g, o, c_t), b_hh must already be folded into P, and
+                    cseq is only touched at slots s_begin (read) and s_end (written). */
 } IpnLstmLayer;
 int ipn_lstm_layer_fwd(const IpnLstmLayer* p, void* stream);
+/* 1 when an LSTM layer of this shape can run the persistent cluster kernels (tcgen05 core, bf16, H = 128 or 256,
+ * B % 128 == 0) */
+int ipn_lstm_persist_eligible(int core, int act_dt, int B, int H);
+/* elements per (timestep, batch row) of `gates`: 4H for the per-step kernels, 5H for the persistent ones */
+int ipn_lstm_gates_cols(int H, int persistent);
 
 typedef struct {
   int core, act_dt;
@@ -301,8 +335,11 @@ typedef struct {
   long long ld_dy;
   int y_col0;
   void* dP; /* [T*B,4H] gradient wrt pre-activations */
-  float* ws; /* workspace fp32 [3 * B * H] */
+  float* ws; /* workspace fp32 [3 * B * H] (per-step kernels only) */
   int y_reverse_time;
+  int gates_persist; /* 1: `gates` was written by the persistent forward kernel (IpnLstmLayer.P_blocked): the whole
+                        reverse-time chain runs as ONE persistent cluster kernel (dY must be non-null, ld_dy % 8 == 0;
+                        hseq / cseq / ws are not read) */
 } IpnLstmLayerBwd;
 int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* p, void* stream);
 

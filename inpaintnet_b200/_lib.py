@@ -43,6 +43,11 @@ class GruInproj(C.Structure):
                 ("H", i32), ("out", vp)]
 
 
+class LstmInproj(C.Structure):
+    _fields_ = [("X", vp), ("ldx", ll), ("K", i32), ("w_ih", vp), ("ldw", ll), ("X2", vp), ("ldx2", ll), ("K2", i32),
+                ("w_ih2", vp), ("ldw2", ll), ("rows", ll), ("b_ih", vp), ("b_hh", vp), ("H", i32), ("out", vp)]
+
+
 class GruLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B_total", i32), ("H", i32), ("row0", i32),
                 ("nrows", i32), ("s_begin", i32), ("s_end", i32), ("ndir", i32), ("dir", GruDir * 2), ("y", vp),
@@ -65,13 +70,13 @@ class LstmLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B", i32), ("H", i32), ("w_hh", vp), ("b_hh", vp),
                 ("P", vp), ("ldP", ll), ("hseq", vp), ("cseq", vp), ("gates", vp), ("y", vp), ("ld_y", ll),
                 ("y_col0", i32), ("y_reverse_time", i32), ("s_begin", i32), ("s_end", i32), ("table", vp),
-                ("ld_table", ll), ("tok_scalar", vp)]
+                ("ld_table", ll), ("tok_scalar", vp), ("P_blocked", i32)]
 
 
 class LstmLayerBwd(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B", i32), ("H", i32), ("w_hh", vp), ("hseq", vp),
                 ("cseq", vp), ("gates", vp), ("dY", vp), ("ld_dy", ll), ("y_col0", i32), ("dP", vp), ("ws", vp),
-                ("y_reverse_time", i32)]
+                ("y_reverse_time", i32), ("gates_persist", i32)]
 
 
 class CeKl(C.Structure):
@@ -92,7 +97,7 @@ class TickDecode(C.Structure):
                 ("use_maps", i32), ("wmap", RowMap), ("smap", RowMap), ("gates_blocked", i32), ("ws", vp), ("ws_bytes", ll)]
 
 
-STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruInproj, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
+STRUCTS_IN_ORDER = [RowMap, GemmSeg, Gemm, GruInproj, LstmInproj, GruDir, GruLayer, GruBwdDir, GruLayerBwd, LstmLayer, LstmLayerBwd, CeKl,
                     PackItem, TickDecode]
 
 # name -> (restype, argtypes); every symbol declared in include/inpaintnet_b200.h
@@ -113,6 +118,9 @@ SYMBOLS = {
     "ipn_gru_layer_bwd_ws_bytes": (ll, [C.POINTER(GruLayerBwd)]),
     "ipn_gru_gates_cols": (i32, [i32]),
     "ipn_gru_persist_eligible": (i32, [i32, i32, i32, i32]),
+    "ipn_lstm_inproj_blocked": (i32, [C.POINTER(LstmInproj), vp]),
+    "ipn_lstm_persist_eligible": (i32, [i32, i32, i32, i32]),
+    "ipn_lstm_gates_cols": (i32, [i32, i32]),
     "ipn_lstm_layer_fwd": (i32, [C.POINTER(LstmLayer), vp]),
     "ipn_lstm_layer_bwd": (i32, [C.POINTER(LstmLayerBwd), vp]),
     "ipn_tokens_time_major": (i32, [vp, i32, i32, i32, vp, vp, vp]),

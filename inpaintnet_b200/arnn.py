@@ -30,18 +30,50 @@ def _round8(x):
 
 
 def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=False, step=None, table=0, tokptr=0,
-                    state=None):
-    """Runs a stack of single-layer LSTMs. names[l] = parameter prefix ('lstm_generation.0.').  P0: tensor [T*B,4H]
-    = input projection of layer 0 incl. b_ih.  step=None: whole sequence; step=t: only timestep t (serial decode); step=(s0, s1): timesteps [s0, s1).
+                    state=None, persist=False):
+    """Runs a stack of single-layer LSTMs. names[l] = parameter prefix ('lstm_generation.0.').
+    persist=False: P0 = tensor [T*B,4H], input projection of layer 0 incl. b_ih; one fused kernel per timestep.
+        step=None: whole sequence; step=t: only timestep t (serial decode); step=(s0, s1): timesteps [s0, s1).
+    persist=True (whole sequence only): P0 = BLOCKED input projection of layer 0 (ops.lstm_inproj_blocked: b_ih + b_hh
+        folded); every layer runs as ONE persistent cluster kernel (W_hh resident in shared memory, h_t exchanged
+        through distributed shared memory) and the projections between the layers are written blocked by the GEMM.
     Returns the state dict (hseq, cseq, gates, y per layer)."""
     dev, act = P0.device, prec.tdt
     L = len(names)
+    if persist:
+        assert step is None and state is None and not table
+        gcols = ops.lstm_gates_cols(H, True)
+        hseq, cseq, gates, ys, Ps = [], [], [], [], [P0]
+        for l in range(L):
+            h = torch.empty((T + 1) * B, H, dtype=act, device=dev)
+            h[:B].zero_()
+            c = torch.empty((T + 1) * B, H, dtype=torch.float32, device=dev)   # only slots 0 and T are touched
+            c[:B].zero_()
+            hseq.append(h)
+            cseq.append(c)
+            gates.append(torch.empty(T * B, gcols, dtype=act, device=dev) if need_grad else None)
+            rev = last_y_reverse and l == L - 1
+            # y_t == h_t: the layer output is the hseq slots 1..T unless it has to be written time-flipped
+            ys.append(torch.empty(T * B, H, dtype=act, device=dev) if rev else h[B:])
+            if l > 0:
+                nm = names[l]
+                w = arena.w(prec, nm + "weight_ih_l0")
+                Pl = torch.empty(T * B, 4 * H, dtype=act, device=dev)
+                ops.lstm_inproj_blocked(ys[l - 1].data_ptr(), H, H, w[0], w[1], T * B, arena.fptr(nm + "bias_ih_l0"),
+                                        arena.fptr(nm + "bias_hh_l0"), H, Pl.data_ptr())
+                Ps.append(Pl)
+            nm = names[l]
+            ops.lstm_layer_fwd(prec, T, B, H, arena.w(prec, nm + "weight_hh_l0")[0], arena.fptr(nm + "bias_hh_l0"),
+                               Ps[l].data_ptr(), 4 * H, h.data_ptr(), c.data_ptr(),
+                               gates=gates[l].data_ptr() if need_grad else 0, y=ys[l].data_ptr() if rev else 0, ld_y=H,
+                               y_reverse_time=1 if rev else 0, P_blocked=1)
+        return dict(hseq=hseq, cseq=cseq, gates=gates, y=ys, P=Ps, persist=True)
     if state is None:
         state = dict(hseq=[torch.zeros((T + 1) * B, H, dtype=act, device=dev) for _ in range(L)],
                      cseq=[torch.zeros((T + 1) * B, H, dtype=torch.float32, device=dev) for _ in range(L)],
                      gates=[torch.empty(T * B, 4 * H, dtype=act, device=dev) if need_grad else None for _ in range(L)],
                      y=[torch.empty(T * B, H, dtype=act, device=dev) for _ in range(L)],
-                     P=[P0] + [torch.empty(T * B, 4 * H, dtype=act, device=dev) for _ in range(L - 1)])
+                     P=[P0] + [torch.empty(T * B, 4 * H, dtype=act, device=dev) for _ in range(L - 1)], persist=False)
     s0, s1 = (0, 0) if step is None else (step if isinstance(step, tuple) else (step, step + 1))
     for l, nm in enumerate(names):
         if l > 0:
@@ -62,15 +94,21 @@ def _lstm_stack_bwd(arena, prec, names, state, dY_last, T, B, H, X0_parts, last_
     Returns dP of layer 0 [T*B,4H] (for the caller's input gradients)."""
     dev, act, es = dY_last.device, prec.tdt, prec.es
     L = len(names)
-    ws = torch.empty(3 * B * H, dtype=torch.float32, device=dev)
+    persist = bool(state.get("persist"))
+    ws = None if persist else torch.empty(3 * B * H, dtype=torch.float32, device=dev)
     dY = dY_last
     dP = None
     for l in range(L - 1, -1, -1):
         nm = names[l]
         dP = torch.empty(T * B, 4 * H, dtype=act, device=dev)
-        ops.lstm_layer_bwd(prec, T, B, H, arena.w(prec, nm + "weight_hh_l0")[0], state["hseq"][l].data_ptr(),
-                           state["cseq"][l].data_ptr(), state["gates"][l].data_ptr(), dY.data_ptr(), H, 0, dP.data_ptr(),
-                           ws.data_ptr(), y_reverse_time=1 if (last_y_reverse and l == L - 1) else 0)
+        rev = 1 if (last_y_reverse and l == L - 1) else 0
+        if persist:
+            ops.lstm_layer_bwd(prec, T, B, H, arena.w(prec, nm + "weight_hh_l0")[0], 0, 0, state["gates"][l].data_ptr(),
+                               dY.data_ptr(), H, 0, dP.data_ptr(), 0, y_reverse_time=rev, gates_persist=1)
+        else:
+            ops.lstm_layer_bwd(prec, T, B, H, arena.w(prec, nm + "weight_hh_l0")[0], state["hseq"][l].data_ptr(),
+                               state["cseq"][l].data_ptr(), state["gates"][l].data_ptr(), dY.data_ptr(), H, 0, dP.data_ptr(),
+                               ws.data_ptr(), y_reverse_time=rev)
         if arena.wants_grad(nm + "weight_hh_l0"):
             _wgrad(prec, dP.data_ptr(), 4 * H, 4 * H, state["hseq"][l].data_ptr(), H, H, T * B, arena.gptr(nm + "weight_hh_l0"), H)
             ops.colsum(dP.data_ptr(), prec.act, 4 * H, T * B, 4 * H, arena.gptr(nm + "bias_ih_l0"),
@@ -223,9 +261,17 @@ class ConstraintModelGaussianReg(Model):
         cnames = [f"lstm_constraint.{l}." for l in range(L)]
         gnames = [f"lstm_generation.{l}." for l in range(L)]
         Pc = torch.empty(T * B, 4 * H, dtype=act, device=dev)
-        _lin(prec, Xc.data_ptr(), ldc, T * B, Ic, arena.w(prec, cnames[0] + "weight_ih_l0"), 4 * H, Pc.data_ptr(), prec.act,
-             4 * H, bias=arena.fptr(cnames[0] + "bias_ih_l0"))
-        cstate = _lstm_stack_fwd(arena, prec, cnames, Pc, T, B, H, need_grad, last_y_reverse=True)
+        # whole-sequence stacks run the persistent cluster kernels when the shape allows (bf16 tensor-core mode,
+        # H = 128 / 256, B % 128 == 0); forward_inpaint mixes a prefix scan with per-tick steps and stays per-step
+        persist = inpaint is None and ops.lstm_persist_eligible(prec, B, H)
+        wc0 = arena.w(prec, cnames[0] + "weight_ih_l0")
+        if persist:
+            ops.lstm_inproj_blocked(Xc.data_ptr(), ldc, Ic, wc0[0], wc0[1], T * B, arena.fptr(cnames[0] + "bias_ih_l0"),
+                                    arena.fptr(cnames[0] + "bias_hh_l0"), H, Pc.data_ptr())
+        else:
+            _lin(prec, Xc.data_ptr(), ldc, T * B, Ic, wc0, 4 * H, Pc.data_ptr(), prec.act, 4 * H,
+                 bias=arena.fptr(cnames[0] + "bias_ih_l0"))
+        cstate = _lstm_stack_fwd(arena, prec, cnames, Pc, T, B, H, need_grad, last_y_reverse=True, persist=persist)
         cout = cstate["y"][L - 1]                                   # [T*B, H] in NORMAL time order
         # ---- generation stack
         w_e = arena.w(prec, gnames[0] + "weight_ih_l0", 0, E)
@@ -244,10 +290,15 @@ class ConstraintModelGaussianReg(Model):
             Xe = torch.zeros(T * B, 16, dtype=act, device=dev)
             ops.gather_cols(arena.fptr("note_embeddings.0.weight"), E, idx.data_ptr(), 1, T * B, Xe.data_ptr(), prec.act, 16, 0,
                             row_scale=scale.data_ptr() if scale is not None else 0)
-            ops.gemm(prec.core, prec.act, T * B, 4 * H,
-                     [(Xe.data_ptr(), 16, 0, w_e[0], w_e[1], 0, E), (cout.data_ptr(), H, 0, w_c[0], w_c[1], 0, H)],
-                     Pg.data_ptr(), prec.act, 4 * H, bias=arena.fptr(gnames[0] + "bias_ih_l0"))
-            gstate = _lstm_stack_fwd(arena, prec, gnames, Pg, T, B, H, need_grad)
+            if persist:
+                ops.lstm_inproj_blocked(Xe.data_ptr(), 16, E, w_e[0], w_e[1], T * B, arena.fptr(gnames[0] + "bias_ih_l0"),
+                                        arena.fptr(gnames[0] + "bias_hh_l0"), H, Pg.data_ptr(),
+                                        X2=cout.data_ptr(), ldx2=H, K2=H, w_ih2=w_c[0], ldw2=w_c[1])
+            else:
+                ops.gemm(prec.core, prec.act, T * B, 4 * H,
+                         [(Xe.data_ptr(), 16, 0, w_e[0], w_e[1], 0, E), (cout.data_ptr(), H, 0, w_c[0], w_c[1], 0, H)],
+                         Pg.data_ptr(), prec.act, 4 * H, bias=arena.fptr(gnames[0] + "bias_ih_l0"))
+            gstate = _lstm_stack_fwd(arena, prec, gnames, Pg, T, B, H, need_grad, persist=persist)
             hid = torch.empty(T * B, Lh, dtype=act, device=dev)
             _lin(prec, gstate["y"][L - 1].data_ptr(), H, T * B, H, arena.w(prec, "linear_1.weight"), Lh, hid.data_ptr(), prec.act,
                  Lh, bias=arena.fptr("linear_1.bias"), act=ACT_RELU)

@@ -149,6 +149,9 @@ struct EpiBlockedP {
     const float* b_ih;
     const float* b_hh;
     int H;
+    int ngates;     // 3 (GRU) or 4 (LSTM) arrays per row tile
+    int half_mask;  // bit g: gate g is a sigmoid gate evaluated as 0.5 tanh(0.5 x) + 0.5 -> stored pre-halved
+    int bhh_mask;   // bit g: b_hh of gate g is folded in (GRU: r, z only -- b_hn stays inside r * (.))
   };
   struct Col {};
   static __device__ __forceinline__ void col_init(const Params&, int, Col&) {}
@@ -160,17 +163,21 @@ struct EpiBlockedP {
     const float4 b0 = *reinterpret_cast<const float4*>(p.b_ih + row0), b1 = *reinterpret_cast<const float4*>(p.b_ih + row0 + 4);
     float f[8] = {acc[0][0] + b0.x, acc[0][1] + b0.y, acc[0][2] + b0.z, acc[0][3] + b0.w,
                   acc[0][4] + b1.x, acc[0][5] + b1.y, acc[0][6] + b1.z, acc[0][7] + b1.w};
-    if (g < 2) {
+    if ((p.bhh_mask >> g) & 1) {
       const float4 c0 = *reinterpret_cast<const float4*>(p.b_hh + row0), c1 = *reinterpret_cast<const float4*>(p.b_hh + row0 + 4);
-      f[0] = 0.5f * (f[0] + c0.x); f[1] = 0.5f * (f[1] + c0.y); f[2] = 0.5f * (f[2] + c0.z); f[3] = 0.5f * (f[3] + c0.w);
-      f[4] = 0.5f * (f[4] + c1.x); f[5] = 0.5f * (f[5] + c1.y); f[6] = 0.5f * (f[6] + c1.z); f[7] = 0.5f * (f[7] + c1.w);
+      f[0] += c0.x; f[1] += c0.y; f[2] += c0.z; f[3] += c0.w;
+      f[4] += c1.x; f[5] += c1.y; f[6] += c1.z; f[7] += c1.w;
+    }
+    if ((p.half_mask >> g) & 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= 0.5f;
     }
     uint4 o;
     __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
     const long long R = col;
-    p.out[(((R >> 7) * 3 + g) * (H >> 3) + (u >> 3)) * 128 + (R & 127)] = o;
+    p.out[(((R >> 7) * p.ngates + g) * (H >> 3) + (u >> 3)) * 128 + (R & 127)] = o;
   }
 };
 

@@ -159,6 +159,50 @@ extern "C" int ipn_gru_inproj_blocked(const IpnGruInproj* q, void* stream_) {
   P.epi.b_ih = q->b_ih;
   P.epi.b_hh = q->b_hh;
   P.epi.H = q->H;
+  P.epi.ngates = 3;
+  P.epi.half_mask = 3;   // r, z
+  P.epi.bhh_mask = 3;
   if (pair) return launch_umma_persist<UmmaPCfg<BR, false, false, true>, EpiBlockedP>(b, 1, N3, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
   return launch_umma_persist<UmmaPCfg<BR, false, false, false>, EpiBlockedP>(b, 1, N3, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
+}
+
+// Blocked LSTM input projection (4 gates, up to two input segments): see include/inpaintnet_b200.h
+extern "C" int ipn_lstm_inproj_blocked(const IpnLstmInproj* q, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IPN_REQUIRE(q != nullptr && q->X && q->w_ih && q->b_ih && q->b_hh && q->out, IPN_ERR_ARG, "lstm_inproj_blocked: null pointer");
+  IPN_PROPAGATE(ensure_device());
+  IPN_REQUIRE(q->rows > 0 && q->rows % 128 == 0 && q->H % 8 == 0 && q->H > 0 && q->K > 0, IPN_ERR_ARG,
+              "lstm_inproj_blocked: rows must be a multiple of 128 and H of 8 (rows=%lld H=%d)", q->rows, q->H);
+  IPN_REQUIRE(q->rows < (1LL << 31), IPN_ERR_ARG, "lstm_inproj_blocked: too many rows");
+  IPN_REQUIRE(q->X2 == nullptr || (q->w_ih2 != nullptr && q->K2 > 0), IPN_ERR_ARG, "lstm_inproj_blocked: bad second segment");
+  constexpr int BR = 256;
+  const int N4 = 4 * q->H;
+  const bool pair = (q->rows / 128) % 2 == 0;
+  UmmaBatch<EpiBlockedP> b;
+  memset(&b, 0, sizeof(b));
+  b.split_k = 1;
+  UmmaProblem<EpiBlockedP>& P = b.p[0];
+  P.nseg = q->X2 != nullptr ? 2 : 1;
+  P.M = N4;
+  P.N = (int)q->rows;
+  P.gate_stride = 0;
+  {
+    HostOperand x{q->w_ih, q->ldw, 0, N4, 0, 0};
+    HostOperand w{q->X, q->ldx, 0, q->rows, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[0], x, w, q->K, pair ? BR / 2 : BR));
+  }
+  if (q->X2 != nullptr) {
+    HostOperand x{q->w_ih2, q->ldw2, 0, N4, 0, 0};
+    HostOperand w{q->X2, q->ldx2, 0, q->rows, 0, 0};
+    IPN_PROPAGATE(fill_umma_seg(P.seg[1], x, w, q->K2, pair ? BR / 2 : BR));
+  }
+  P.epi.out = reinterpret_cast<uint4*>(q->out);
+  P.epi.b_ih = q->b_ih;
+  P.epi.b_hh = q->b_hh;
+  P.epi.H = q->H;
+  P.epi.ngates = 4;
+  P.epi.half_mask = 1 | 2 | 8;   // i, f, o
+  P.epi.bhh_mask = 15;
+  if (pair) return launch_umma_persist<UmmaPCfg<BR, false, false, true>, EpiBlockedP>(b, 1, N4, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
+  return launch_umma_persist<UmmaPCfg<BR, false, false, false>, EpiBlockedP>(b, 1, N4, (int)q->rows, stream, "gemm_umma_inproj_blocked", 1);
 }

@@ -16,6 +16,9 @@ __global__ void lstm_bwd_point_kernel(LstmBwdPoint p, int nrows) {
   lstm_bwd_pointwise<W>(p, col, row0, min(W, nrows - row0), dh);
 }
 
+int lstm_persist_fwd(const IpnLstmLayer* L, int s_begin, int s_end, cudaStream_t stream);   // lstm_persist.cu
+int lstm_persist_bwd(const IpnLstmLayerBwd* L, cudaStream_t stream);
+
 static int check_lstm(int core, int act_dt, int T, int B, int H) {
   IPN_REQUIRE(core == IPN_CORE_SIMT || core == IPN_CORE_UMMA, IPN_ERR_ARG, "lstm: unknown core %d", core);
   IPN_REQUIRE(core != IPN_CORE_UMMA || act_dt == IPN_BF16, IPN_ERR_ARG, "lstm: the tcgen05 core needs bf16 activations");
@@ -40,6 +43,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   const int s_begin = L->s_begin, s_end = L->s_end > 0 ? L->s_end : T;
   IPN_REQUIRE(0 <= s_begin && s_begin < s_end && s_end <= T, IPN_ERR_ARG, "lstm_layer_fwd: bad step range");
   IPN_REQUIRE(!L->table || L->tok_scalar, IPN_ERR_ARG, "lstm_layer_fwd: table without token");
+  if (L->P_blocked) return lstm_persist_fwd(L, s_begin, s_end, stream);
   auto fill_epi = [&](EpiLstmFwd::Params& e, int s) {
     e.H = H; e.act_dt = dt; e.trow = s * B;
     e.P = L->P; e.ldP = L->ldP; e.b_hh = L->b_hh;
@@ -87,6 +91,10 @@ extern "C" int ipn_lstm_layer_bwd(const IpnLstmLayerBwd* L, void* stream_) {
   IPN_REQUIRE(L != nullptr, IPN_ERR_ARG, "lstm_layer_bwd: null descriptor");
   IPN_PROPAGATE(ensure_device());
   IPN_PROPAGATE(check_lstm(L->core, L->act_dt, L->T, L->B, L->H));
+  if (L->gates_persist) {
+    IPN_REQUIRE(L->w_hh && L->gates && L->dP, IPN_ERR_ARG, "lstm_layer_bwd: null pointer");
+    return lstm_persist_bwd(L, stream);
+  }
   IPN_REQUIRE(L->w_hh && L->hseq && L->cseq && L->gates && L->dP && L->ws, IPN_ERR_ARG, "lstm_layer_bwd: null pointer");
   const int T = L->T, H = L->H, dt = L->act_dt;
   const long long B = L->B;

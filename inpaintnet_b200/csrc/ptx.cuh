@@ -250,6 +250,54 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
+// ---------------- thread-block clusters: distributed shared memory ----------------
+// shared::cluster address of `saddr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(caddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// arrive on an mbarrier of any CTA of the cluster (caddr from mapa); release at cluster scope: the data this thread
+// (and, through a preceding __syncwarp, its warp) wrote to that CTA's shared memory is visible to an acquire.cluster waiter
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded like mbar_wait; acquire at cluster scope (pairs with mbar_arrive_cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3FF) == 0 && clock64() - t0 > 8000000000LL) {
+      printf("inpaintnet_b200: cluster mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// arrives on the mbarrier at this offset in every CTA of `cta_mask` once all MMAs issued so far by this thread are done
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // ---------------- UMMA descriptors ----------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, bf16.
 //  K-major  tile [rows][64 elems=128B], 8-row groups of 1024B: LBO(enc)=1, SBO = 1024B.

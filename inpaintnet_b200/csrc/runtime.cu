@@ -184,7 +184,7 @@ const char* ipn_last_error(void) { return ipn::g_err; }
 int ipn_abi_version(void) { return IPN_ABI_VERSION; }
 int ipn_struct_sizes(int* out_host, int n) {
   const int sizes[] = {(int)sizeof(IpnRowMap),      (int)sizeof(IpnGemmSeg),  (int)sizeof(IpnGemm),
-                       (int)sizeof(IpnGruInproj),   (int)sizeof(IpnGruDir),      (int)sizeof(IpnGruLayer), (int)sizeof(IpnGruBwdDir),
+                       (int)sizeof(IpnGruInproj),   (int)sizeof(IpnLstmInproj),  (int)sizeof(IpnGruDir),      (int)sizeof(IpnGruLayer), (int)sizeof(IpnGruBwdDir),
                        (int)sizeof(IpnGruLayerBwd), (int)sizeof(IpnLstmLayer), (int)sizeof(IpnLstmLayerBwd),
                        (int)sizeof(IpnCeKl),        (int)sizeof(IpnPackItem), (int)sizeof(IpnTickDecode)};
   const int m = (int)(sizeof(sizes) / sizeof(sizes[0]));

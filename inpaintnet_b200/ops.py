@@ -154,9 +154,27 @@ def gru_layer_bwd(prec, T, B_total, H, dirs, dhz_ws, dY=0, ld_dy=0, mask=0, ld_m
     L.check(lib().ipn_gru_layer_bwd(C.byref(p), stream()))
 
 
+def lstm_persist_eligible(prec, B, H):
+    return bool(lib().ipn_lstm_persist_eligible(prec.core, prec.act, B, H))
+
+
+def lstm_gates_cols(H, persistent):
+    return lib().ipn_lstm_gates_cols(H, 1 if persistent else 0)
+
+
+def lstm_inproj_blocked(X, ldx, K, w_ih, ldw, rows, b_ih, b_hh, H, out, X2=0, ldx2=0, K2=0, w_ih2=0, ldw2=0):
+    """Blocked bf16 [rows, 4, H] input projection of an LSTM layer (up to two input segments)."""
+    p = L.LstmInproj()
+    p.X, p.ldx, p.K, p.w_ih, p.ldw = X, ldx, K, w_ih, ldw
+    p.X2, p.ldx2, p.K2, p.w_ih2, p.ldw2 = X2 or None, ldx2, K2, w_ih2 or None, ldw2
+    p.rows, p.b_ih, p.b_hh, p.H, p.out = rows, b_ih, b_hh, H, out
+    L.check(lib().ipn_lstm_inproj_blocked(C.byref(p), stream()))
+
+
 def lstm_layer_fwd(prec, T, B, H, w_hh, b_hh, P, ldP, hseq, cseq, gates=0, y=0, ld_y=0, y_col0=0, y_reverse_time=0,
-                   s_begin=0, s_end=0, table=0, ld_table=0, tok_scalar=0):
+                   s_begin=0, s_end=0, table=0, ld_table=0, tok_scalar=0, P_blocked=0):
     p = L.LstmLayer()
+    p.P_blocked = P_blocked
     p.y_reverse_time, p.s_begin, p.s_end = y_reverse_time, s_begin, s_end
     p.table, p.ld_table, p.tok_scalar = table or None, ld_table, tok_scalar or None
     p.core, p.act_dt, p.T, p.B, p.H = prec.core, prec.act, T, B, H
@@ -165,11 +183,11 @@ def lstm_layer_fwd(prec, T, B, H, w_hh, b_hh, P, ldP, hseq, cseq, gates=0, y=0, 
     L.check(lib().ipn_lstm_layer_fwd(C.byref(p), stream()))
 
 
-def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP, ws, y_reverse_time=0):
+def lstm_layer_bwd(prec, T, B, H, w_hh, hseq, cseq, gates, dY, ld_dy, y_col0, dP, ws, y_reverse_time=0, gates_persist=0):
     p = L.LstmLayerBwd()
-    p.y_reverse_time = y_reverse_time
+    p.y_reverse_time, p.gates_persist = y_reverse_time, gates_persist
     p.core, p.act_dt, p.T, p.B, p.H = prec.core, prec.act, T, B, H
-    p.w_hh, p.hseq, p.cseq, p.gates, p.dY, p.ld_dy, p.y_col0, p.dP, p.ws = w_hh, hseq, cseq, gates, dY or None, ld_dy, y_col0, dP, ws
+    p.w_hh, p.hseq, p.cseq, p.gates, p.dY, p.ld_dy, p.y_col0, p.dP, p.ws = w_hh, hseq or None, cseq or None, gates, dY or None, ld_dy, y_col0, dP, ws or None
     L.check(lib().ipn_lstm_layer_bwd(C.byref(p), stream()))
 
 

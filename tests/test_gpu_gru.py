@@ -173,6 +173,86 @@ def test_lstm_layer_fwd_bwd(prec_name, H, B, T):
     assert (dX.cpu() - dx_ref).abs().max() <= a * max(1.0, dx_ref.abs().max().item())
 
 
+@pytest.mark.parametrize("H,B,T,rev", [(256, 128, 3, 0), (256, 384, 9, 1), (128, 256, 7, 0), (256, 4096, 24, 0)])
+def test_lstm_persistent_cluster_layer_fwd_bwd(H, B, T, rev):
+    """Persistent LSTM layer (thread-block cluster of H/64 CTAs per 128-row tile, W_hh resident in shared memory, h_t
+    exchanged through distributed shared memory, cell state in registers): blocked two-segment input projection,
+    forward outputs / final cell state and the backward pass (dP -> dW_hh, db, dX) against the oracle's autograd."""
+    prec = Precision("bf16")
+    assert ops.lstm_persist_eligible(prec, B, H)
+    I1, I2 = 10, 64
+    W = _weights(H, I1 + I2, 31, G=4)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, I1 + I2, generator=g)
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    Wr = {k: v.clone().requires_grad_() for k, v in W.items()}
+    xr = x.clone().requires_grad_()
+    xin = torch.flip(rnd(xr), [1]) if rev else rnd(xr)       # rev: the layer runs on the time-flipped sequence ...
+    y_ref = O.lstm_layer(xin, rnd(Wr["w_ih"]), rnd(Wr["w_hh"]), Wr["b_ih"], Wr["b_hh"])
+    if rev:
+        y_ref = torch.flip(y_ref, [1])                        # ... and its output is flipped back (arnn_model.py:455-475)
+    gy = torch.randn(B, T, H, generator=g)
+    (y_ref * gy).sum().backward()
+    x_seq = torch.flip(x, [1]) if rev else x
+    x_tm = x_seq.transpose(0, 1).reshape(T * B, I1 + I2)
+    X1 = torch.zeros(T * B, 16, dtype=torch.bfloat16, device=DEV)
+    X1[:, :I1] = x_tm[:, :I1].to(DEV)
+    X2 = x_tm[:, I1:].contiguous().to(device=DEV, dtype=torch.bfloat16)
+    w1 = torch.zeros(4 * H, 16, dtype=torch.bfloat16, device=DEV)
+    w1[:, :I1] = W["w_ih"][:, :I1].to(DEV)
+    w2 = W["w_ih"][:, I1:].contiguous().to(device=DEV, dtype=torch.bfloat16)
+    whh = _to_dev(W["w_hh"], prec)
+    bih, bhh = W["b_ih"].to(DEV), W["b_hh"].to(DEV)
+    P = torch.empty(T * B, 4 * H, dtype=torch.bfloat16, device=DEV)
+    ops.lstm_inproj_blocked(X1.data_ptr(), 16, I1, w1.data_ptr(), 16, T * B, bih.data_ptr(), bhh.data_ptr(), H, P.data_ptr(),
+                            X2=X2.data_ptr(), ldx2=I2, K2=I2, w_ih2=w2.data_ptr(), ldw2=I2)
+    # blocked layout check of the projection itself: vec16(R, g, u) = ((R/128*4 + g)*(H/8) + u/8)*128 + R%128
+    torch.cuda.synchronize()
+    pre = (rnd(x_tm) @ rnd(W["w_ih"]).t() + W["b_ih"] + W["b_hh"]).view(T * B // 128, 128, 4, H // 8, 8)
+    pre = pre * torch.tensor([0.5, 0.5, 1.0, 0.5]).view(1, 1, 4, 1, 1)
+    blk = P.float().cpu().view(T * B // 128, 4, H // 8, 128, 8).permute(0, 3, 1, 2, 4)
+    assert torch.allclose(blk, pre, atol=3e-2, rtol=2e-2), (blk - pre).abs().max()
+    hseq = torch.empty((T + 1) * B, H, dtype=torch.bfloat16, device=DEV)
+    hseq[:B].zero_()
+    cseq = torch.empty((T + 1) * B, H, dtype=torch.float32, device=DEV)
+    cseq[:B].zero_()
+    gates = torch.empty(T * B, ops.lstm_gates_cols(H, True), dtype=torch.bfloat16, device=DEV)
+    y = torch.empty(T * B, H, dtype=torch.bfloat16, device=DEV)
+    ops.lstm_layer_fwd(prec, T, B, H, whh.data_ptr(), bhh.data_ptr(), P.data_ptr(), 4 * H, hseq.data_ptr(), cseq.data_ptr(),
+                       gates=gates.data_ptr(), y=y.data_ptr(), ld_y=H, y_reverse_time=rev, P_blocked=1)
+    torch.cuda.synchronize()
+    tol = dict(atol=3e-2, rtol=3e-2)
+    y_lib = y.float().cpu().view(T, B, H).transpose(0, 1)
+    assert torch.allclose(y_lib, y_ref.detach(), **tol), (y_lib - y_ref).abs().max()
+    h_lib = hseq[B:].float().cpu().view(T, B, H).transpose(0, 1)          # processing order
+    assert torch.allclose(torch.flip(h_lib, [1]) if rev else h_lib, y_ref.detach(), **tol)
+    # no-grad variant (no saved state) gives the same outputs
+    y2 = torch.empty_like(y)
+    hseq2, cseq2 = hseq.clone(), cseq.clone()
+    ops.lstm_layer_fwd(prec, T, B, H, whh.data_ptr(), bhh.data_ptr(), P.data_ptr(), 4 * H, hseq2.data_ptr(), cseq2.data_ptr(),
+                       y=y2.data_ptr(), ld_y=H, y_reverse_time=rev, P_blocked=1)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y) and torch.equal(cseq2[T * B:], cseq[T * B:])
+    # ---- backward
+    dY = _to_dev(gy.transpose(0, 1).reshape(T * B, H), prec)            # gradient wrt y in the order y was written
+    dP = torch.empty(T * B, 4 * H, dtype=torch.bfloat16, device=DEV)
+    ops.lstm_layer_bwd(prec, T, B, H, whh.data_ptr(), 0, 0, gates.data_ptr(), dY.data_ptr(), H, 0, dP.data_ptr(), 0,
+                       y_reverse_time=rev, gates_persist=1)
+    gW_hh = torch.zeros(4 * H, H, device=DEV)
+    gb = torch.zeros(4 * H, device=DEV)
+    gW2 = torch.zeros(4 * H, I2, device=DEV)
+    ops.gemm(prec.core, prec.act, 4 * H, H, [(dP.data_ptr(), 4 * H, 1, hseq.data_ptr(), H, 1, T * B)], gW_hh.data_ptr(), F32, H,
+             accumulate=ops.ATOMIC_ADD)
+    ops.gemm(prec.core, prec.act, 4 * H, I2, [(dP.data_ptr(), 4 * H, 1, X2.data_ptr(), I2, 1, T * B)], gW2.data_ptr(), F32, I2,
+             accumulate=ops.ATOMIC_ADD)
+    ops.colsum(dP.data_ptr(), prec.act, 4 * H, T * B, 4 * H, gb.data_ptr())
+    torch.cuda.synchronize()
+    a = 6e-2
+    for mine, ref, what in ((gW_hh, Wr["w_hh"].grad, "dW_hh"), (gb, Wr["b_ih"].grad, "db"), (gW2, Wr["w_ih"].grad[:, I1:], "dW_ih")):
+        err = (mine.cpu() - ref).norm() / ref.norm().clamp_min(1e-9)
+        assert err < a, (what, float(err))
+
+
 @pytest.mark.parametrize("H,B,T,V", [(512, 512, 7, 64), (128, 256, 5, 11), (64, 128, 3, 128), (320, 384, 4, 90)])
 def test_persistent_layer_token_table_gather_is_bit_exact(H, B, T, V):
     """Encoder layer 0: the input projection is a row of a token table.  With table_rows given the blocked P of the

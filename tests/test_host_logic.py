@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.ipn_abi_version() == 2
+    assert lib.ipn_abi_version() == 3
 
 
 def test_no_cpu_fallback():
