@@ -316,6 +316,9 @@ typedef struct {
                     distributed shared memory once per step.  `gates` then has ipn_lstm_gates_cols(H) columns in a
                     layout private to the fwd/bwd pair (i, f, g, o, c_t), b_hh must already be folded into P, and
                     cseq is only touched at slots s_begin (read) and s_end (written). */
+  int gates_blocked; /* per-step kernels only: write `gates` (ipn_lstm_gates_cols(H, 1) columns) in the persistent
+                        kernels' private layout, so that ipn_lstm_layer_bwd can run with gates_persist = 1 on a layer
+                        whose forward had to run tick by tick (token feedback); needs ipn_lstm_persist_eligible */
 } IpnLstmLayer;
 int ipn_lstm_layer_fwd(const IpnLstmLayer* p, void* stream);
 /* 1 when an LSTM layer of this shape can run the persistent cluster kernels (tcgen05 core, bf16, H = 128 or 256,

@@ -70,7 +70,7 @@ class LstmLayer(C.Structure):
     _fields_ = [("core", i32), ("act_dt", i32), ("T", i32), ("B", i32), ("H", i32), ("w_hh", vp), ("b_hh", vp),
                 ("P", vp), ("ldP", ll), ("hseq", vp), ("cseq", vp), ("gates", vp), ("y", vp), ("ld_y", ll),
                 ("y_col0", i32), ("y_reverse_time", i32), ("s_begin", i32), ("s_end", i32), ("table", vp),
-                ("ld_table", ll), ("tok_scalar", vp), ("P_blocked", i32)]
+                ("ld_table", ll), ("tok_scalar", vp), ("P_blocked", i32), ("gates_blocked", i32)]
 
 
 class LstmLayerBwd(C.Structure):

@@ -30,10 +30,12 @@ def _round8(x):
 
 
 def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=False, step=None, table=0, tokptr=0,
-                    state=None, persist=False):
+                    state=None, persist=False, gates_blocked=False):
     """Runs a stack of single-layer LSTMs. names[l] = parameter prefix ('lstm_generation.0.').
     persist=False: P0 = tensor [T*B,4H], input projection of layer 0 incl. b_ih; one fused kernel per timestep.
         step=None: whole sequence; step=t: only timestep t (serial decode); step=(s0, s1): timesteps [s0, s1).
+        gates_blocked: the saved gates are written in the persistent kernels' layout (the backward pass then runs
+        the persistent cluster kernel although the forward ran tick by tick).
     persist=True (whole sequence only): P0 = BLOCKED input projection of layer 0 (ops.lstm_inproj_blocked: b_ih + b_hh
         folded); every layer runs as ONE persistent cluster kernel (W_hh resident in shared memory, h_t exchanged
         through distributed shared memory) and the projections between the layers are written blocked by the GEMM.
@@ -69,11 +71,13 @@ def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=F
                                y_reverse_time=1 if rev else 0, P_blocked=1)
         return dict(hseq=hseq, cseq=cseq, gates=gates, y=ys, P=Ps, persist=True)
     if state is None:
+        gcols = ops.lstm_gates_cols(H, True) if gates_blocked else 4 * H
         state = dict(hseq=[torch.zeros((T + 1) * B, H, dtype=act, device=dev) for _ in range(L)],
                      cseq=[torch.zeros((T + 1) * B, H, dtype=torch.float32, device=dev) for _ in range(L)],
-                     gates=[torch.empty(T * B, 4 * H, dtype=act, device=dev) if need_grad else None for _ in range(L)],
+                     gates=[torch.empty(T * B, gcols, dtype=act, device=dev) if need_grad else None for _ in range(L)],
                      y=[torch.empty(T * B, H, dtype=act, device=dev) for _ in range(L)],
-                     P=[P0] + [torch.empty(T * B, 4 * H, dtype=act, device=dev) for _ in range(L - 1)], persist=False)
+                     P=[P0] + [torch.empty(T * B, 4 * H, dtype=act, device=dev) for _ in range(L - 1)],
+                     persist=bool(gates_blocked and need_grad), gates_blocked=bool(gates_blocked and need_grad))
     s0, s1 = (0, 0) if step is None else (step if isinstance(step, tuple) else (step, step + 1))
     for l, nm in enumerate(names):
         if l > 0:
@@ -84,7 +88,8 @@ def _lstm_stack_fwd(arena, prec, names, P0, T, B, H, need_grad, last_y_reverse=F
                            state["P"][l].data_ptr(), 4 * H, state["hseq"][l].data_ptr(), state["cseq"][l].data_ptr(),
                            gates=state["gates"][l].data_ptr() if need_grad else 0, y=state["y"][l].data_ptr(), ld_y=H,
                            y_reverse_time=1 if (last_y_reverse and l == L - 1) else 0, s_begin=s0, s_end=s1,
-                           table=table if l == 0 else 0, ld_table=4 * H, tok_scalar=tokptr if l == 0 else 0)
+                           table=table if l == 0 else 0, ld_table=4 * H, tok_scalar=tokptr if l == 0 else 0,
+                           gates_blocked=1 if state.get("gates_blocked") else 0)
     return state
 
 
@@ -320,7 +325,7 @@ class ConstraintModelGaussianReg(Model):
             w1, wo = arena.w(prec, "linear_1.weight"), arena.w(prec, "linear_ouput_notes.0.weight")
             for t in range(T):
                 gstate = _lstm_stack_fwd(arena, prec, gnames, Pg, T, B, H, need_grad, step=t, table=table.data_ptr(),
-                                         tokptr=tokens_in.data_ptr() + 4 * t, state=gstate)
+                                         tokptr=tokens_in.data_ptr() + 4 * t, state=gstate, gates_blocked=persist)
                 yo = gstate["y"][L - 1].data_ptr() + es * t * B * H
                 _lin(prec, yo, H, B, H, w1, Lh, hid.data_ptr() + es * t * B * Lh, prec.act, Lh, bias=arena.fptr("linear_1.bias"),
                      act=ACT_RELU)

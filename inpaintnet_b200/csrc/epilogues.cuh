@@ -633,6 +633,7 @@ struct EpiLstmFwd {
     const float* table;
     long long ld_table;
     const int* tok_scalar;
+    int gates_blocked;  // write `gates` in the persistent kernels' blocked 5-array layout (i, f, g, o, c_t; bf16)
   };
   struct Col {
     float b[4];
@@ -683,7 +684,17 @@ struct EpiLstmFwd {
         const float h = go * tanhf(c);
         p.c_out[R * H + col] = c;
         st_act(p.h_out, R * H + col, h, dt);
-        if (p.gates != nullptr) {
+        if (p.gates != nullptr && p.gates_blocked) {
+          // element (row TR, array a, unit col) of the blocked layout (gru_persist.cuh), so that the backward pass
+          // can run the persistent cluster kernel (lstm_persist.cu) on a layer whose forward ran tick by tick
+          __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(p.gates);
+          const long long vpr = H >> 3;
+          const long long e0 = ((((TR >> 7) * 5) * vpr + (col >> 3)) * 128 + (TR & 127)) * 8 + (col & 7);
+          const long long as = vpr * 128 * 8;
+          gb[e0] = __float2bfloat16_rn(gi); gb[e0 + as] = __float2bfloat16_rn(gf);
+          gb[e0 + 2 * as] = __float2bfloat16_rn(gg); gb[e0 + 3 * as] = __float2bfloat16_rn(go);
+          gb[e0 + 4 * as] = __float2bfloat16_rn(c);
+        } else if (p.gates != nullptr) {
           const long long o = TR * 4 * H + col;
           st_act(p.gates, o, gi, dt); st_act(p.gates, o + H, gf, dt);
           st_act(p.gates, o + 2 * H, gg, dt); st_act(p.gates, o + 3 * H, go, dt);

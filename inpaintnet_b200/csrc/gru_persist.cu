@@ -112,7 +112,7 @@ __global__ void gru_mask_y_kernel(__nv_bfloat16* y, long long ld_y, const unsign
 // ---------------------------------------------------------------------------------------------
 constexpr int GPF_W_BYTES = 3 * GP_CH * 128;  // one (chunk, k-block) of W_hh: 3 gates x 64 rows x 64 bf16 = 24 KB
 constexpr int GPF_W_RING = 3 * GPF_W_BYTES;   // shared memory of the W ring (3 stages; 6 half-size stages per CTA of a pair)
-constexpr int GPF_NBAR = 48;
+constexpr int GPF_NBAR = 56;
 
 static inline int gpf_smem_bytes(int H) {
   return (H / 64) * GP_KB_BYTES + GPF_W_RING + GP_KB_BYTES + H * 4 + GPF_NBAR * 8 + 16;
@@ -121,8 +121,15 @@ static inline int gpf_smem_bytes(int H) {
 // PAIR: two CTAs (adjacent row tiles of one direction) form a cta_group::2 pair: one tcgen05.mma covers both
 // tiles (M = 256), each CTA stages only HALF of every W_hh tile (half the L2 traffic and shared-memory fill,
 // twice the pipeline depth) and the operand fetch per MMA drops from 10 KB to 7 KB per SM.
-template <bool SAVE, bool PAIR>
+// CS = 2 (on by default since round 2, IPN_GPF_CS=0 disables; validated on B200: tests/dev/persist_fwd.py + the GPU suite): COLUMN SPLIT.
+// The two CTAs of a cluster own the SAME 128-row tile and half of the hidden units each (chunks
+// [rank*KB/2, (rank+1)*KB/2): half of the W_hh stream, of the MMAs and of the epilogue per step), so the serial
+// per-step latency halves and a 64-CTA encoder layer occupies 128 SMs.  Every CTA still needs the full h_{t-1}
+// as its A operand: each stores its half of h_t to the hseq slot (TMA store, as before) and signals the PEER's
+// h_stored[chunk] barrier once the store has completed; the A loaders reload all k-blocks from L2 as before.
+template <bool SAVE, bool PAIR, int CS>
 __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __grid_constant__ GruPersistFwd p) {
+  static_assert(CS == 1 || (CS == 2 && !PAIR), "column split uses plain (cta_group::1) MMAs");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int WST_BYTES = PAIR ? GPF_W_BYTES / 2 : GPF_W_BYTES;  // per-CTA bytes of one W stage
   constexpr int WSTAGES = GPF_W_RING / WST_BYTES;
@@ -131,10 +138,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   const int H = p.H, KB = H >> 6, T = p.T;
   const int NS = p.s_end - p.s_begin;   // processing steps s_begin .. s_end-1 (loop index t = s - s_begin)
   const int Bt = p.Bt;
-  const int rbase = p.row0 + blockIdx.x * GP_ROWS;
+  const int tile_x = CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x;   // row tile of this CTA
+  const int rbase = p.row0 + tile_x * GP_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
+  const uint32_t crank = (PAIR || CS > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t rank = PAIR ? crank : 0u;          // pair: which half of the M = 256 tile / of every W stage
+  const bool leader = rank == 0;                    // column split: both CTAs run their own complete pipeline
+  const int c_lo = CS > 1 ? (int)crank * (KB / CS) : 0, c_hi = c_lo + KB / CS;   // chunks (64 hidden units) of this CTA
 
   uint8_t* sA = smem;
   uint8_t* sW = sA + KB * GP_KB_BYTES;
@@ -151,6 +161,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   uint64_t* stg_ready = bars + 40;    // staging tile written by the 8 epilogue warps
   uint64_t* stg_free = bars + 41;     // staging tile read out by the TMA store
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  // column split: the h_stored barriers of ODD steps.  A peer signals them remotely, so nothing in THIS CTA orders
+  // its arrival for step t+1 after our wait for step t; with one barrier set per step parity the peer would have to
+  // be two steps ahead to alias a phase, which the data dependence (it needs our step t+1 stores) rules out.
+  uint64_t* h_stored_odd = bars + 44;  // [8]
 
   if ((ptx::smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("inpaintnet_b200: gru_persist_fwd: shared memory base not 1024-byte aligned\n");
@@ -160,6 +174,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
     if (lane == 0) {
       for (int s = 0; s < 6; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
       for (int k = 0; k < 8; ++k) { ptx::mbar_init(&a_full[k], 1); ptx::mbar_init(&a_free[k], 1); ptx::mbar_init(&h_stored[k], 1); }
+      if (CS > 1) for (int k = 0; k < 8; ++k) ptx::mbar_init(&h_stored_odd[k], 1);
       for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], PAIR ? 32 : 16); }
       ptx::mbar_init(stg_ready, 16);
       ptx::mbar_init(stg_free, 1);
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   for (int u = threadIdx.x; u < H; u += GP_THREADS) sBias[u] = D.b_hh[2 * H + u];
   ptx::tc_fence_before();
   __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  if (PAIR || CS > 1) ptx::cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp < 4) {
@@ -190,19 +205,19 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       auto prefetch_p = [&](int t, int c) {
         if (t >= NS || (p.dbg & 16) || D.Pblk == nullptr) return;
         const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
-        const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
+        const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + tile_x;
         const int vpr = H >> 3;
 #pragma unroll
         for (int g = 0; g < 3; ++g)
           ptx::bulk_prefetch_l2(D.Pblk + ((rt * 3 + g) * vpr + c * 8) * 128, 8 * 128 * 16);
       };
-      prefetch_p(0, 0);
+      prefetch_p(0, c_lo);
       for (int t = 0; t < NS; ++t)
-        for (int c = 0; c < KB; ++c)
+        for (int c = c_lo; c < c_hi; ++c)
           for (int kb = 0; kb < KB; ++kb) {
-            if (kb == 0) prefetch_p(c + 1 == KB ? t + 1 : t, c + 1 == KB ? 0 : c + 1);
+            if (kb == 0) prefetch_p(c + 1 == c_hi ? t + 1 : t, c + 1 == c_hi ? c_lo : c + 1);
             ptx::mbar_wait(&w_empty[stage], phase ^ 1);
-            const bool skip = (p.dbg & 8) && (t > 0 || c > 0);
+            const bool skip = (p.dbg & 8) && (t > 0 || c > c_lo);
             if (leader) {
               if (skip) ptx::mbar_arrive(&w_full[stage]);
               else ptx::mbar_arrive_expect_tx(&w_full[stage], GPF_W_BYTES);
@@ -230,13 +245,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       const uint64_t descA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024);
       const uint64_t descW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024);
       for (int t = 0; t < NS; ++t)
-        for (int c = 0; c < KB; ++c, ++i) {
+        for (int c = c_lo; c < c_hi; ++c, ++i) {
           const int b = i & 1, n = i >> 1;
           wait_acc(&tmem_empty[b], (n & 1) ^ 1, tm, w_te);
           ptx::tc_fence_after();
           const uint32_t dcol = tmem_base + (uint32_t)(b * 256);
           for (int kb = 0; kb < KB; ++kb) {
-            if (c == 0) wait_acc(&a_full[kb], t & 1, tm, w_af);
+            if (c == c_lo) wait_acc(&a_full[kb], t & 1, tm, w_af);
             wait_acc(&w_full[stage], phase, tm, w_wf);
             ptx::tc_fence_after();
             const uint64_t da0 = descA0 + (uint64_t)((kb * GP_KB_BYTES) >> 4);
@@ -249,10 +264,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
               }
               if (PAIR) {
                 ptx::umma_commit_pair(&w_empty[stage]);
-                if (c == KB - 1) ptx::umma_commit_pair(&a_free[kb]);
+                if (c == c_hi - 1) ptx::umma_commit_pair(&a_free[kb]);
               } else {
                 ptx::umma_commit(&w_empty[stage]);
-                if (c == KB - 1) ptx::umma_commit(&a_free[kb]);
+                if (c == c_hi - 1) ptx::umma_commit(&a_free[kb]);
               }
             }
             __syncwarp();
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       for (int t = 0; t < NS; ++t) {
         const int tt = D.reverse ? T - 1 - (p.s_begin + t) : (p.s_begin + t);
         const int out_slot = D.reverse ? tt : tt + 1;
-        for (int c = 0; c < KB; ++c, ++i) {
+        for (int c = c_lo; c < c_hi; ++c, ++i) {
           wait_acc(stg_ready, i & 1, tm, w_sr);
           const long long ts0 = tm ? clock64() : 0;
           ptx::tma_store_2d(&D.tmH, sStg, c * 64, out_slot * Bt + rbase);
@@ -287,7 +302,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           ptx::bulk_wait_read0();
           ptx::mbar_arrive(stg_free);
           ptx::bulk_wait0();
-          ptx::mbar_arrive(&h_stored[c]);
+          if (CS > 1) {   // the peer reloads this chunk of h_t from L2 as a k-block of its next step's A operand
+            uint64_t* hs = (t & 1) ? &h_stored_odd[c] : &h_stored[c];
+            ptx::mbar_arrive(hs);
+            __threadfence();
+            ptx::mbar_arrive_remote_release(hs, crank ^ 1u);
+          } else {
+            ptx::mbar_arrive(&h_stored[c]);
+          }
           if (tm) w_st += clock64() - ts0;
         }
       }
@@ -307,7 +329,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
         for (int kb = 0; kb < KB; ++kb) {
           if (t > 0) {
             wait_acc(&a_free[kb], (t - 1) & 1, tm, w_fr);
-            wait_acc(&h_stored[kb], (t - 1) & 1, tm, w_hs);
+            if (CS > 1) {   // step t-1's stores: barrier set (t-1) & 1, phase ((t-1) >> 1) & 1; peer chunks at cluster scope
+              uint64_t* hs = ((t - 1) & 1) ? &h_stored_odd[kb] : &h_stored[kb];
+              if (kb < c_lo || kb >= c_hi) ptx::mbar_wait_cluster(hs, ((t - 1) >> 1) & 1);
+              else wait_acc(hs, ((t - 1) >> 1) & 1, tm, w_hs);
+            } else {
+              wait_acc(&h_stored[kb], (t - 1) & 1, tm, w_hs);
+            }
             ptx::fence_proxy_async_all();
           }
           if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], PAIR ? 2 * GP_KB_BYTES : GP_KB_BYTES);
@@ -351,7 +379,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           for (int v = 0; v < 2; ++v) dst[g][v] = ldp ? __ldg(base + g * vpr + v) : make_uint4(0, 0, 0, 0);
         return;
       }
-      const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + blockIdx.x;
+      const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + tile_x;
       const uint4* base = D.Pblk + (rt * 3 * vpr + c * 8 + sub * 2) * 128 + row;
 #pragma unroll
       for (int g = 0; g < 3; ++g)
@@ -422,11 +450,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       }
     };
     {
-      int i = 0, t = 0, c = 0;
-      const int total = NS * KB;
+      int i = 0, t = 0, c = c_lo;
+      const int total = NS * (c_hi - c_lo);
       while (i < total) {
         do_chunk(t, c, i);
-        ++i; if (++c == KB) { c = 0; ++t; }
+        ++i; if (++c == c_hi) { c = c_lo; ++t; }
       }
     }
     if (tm) {
@@ -436,7 +464,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();  // the peer's shared memory / TMEM / barriers stay alive until both are done
+  if (PAIR || CS > 1) ptx::cluster_sync_all();  // the peer's shared memory / TMEM / barriers stay alive until both are done
   if (warp == 1) {
     ptx::tc_fence_after();
     if (PAIR) ptx::tmem_dealloc_pair<512>(tmem_base);
@@ -501,10 +529,15 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   const int NS = L->s_end - L->s_begin, ntw = L->nrows / GP_ROWS;   // steps and row tiles of this call's window
   static const int dbg = getenv("IPN_GPF_DBG") ? atoi(getenv("IPN_GPF_DBG")) : 0;
   p.dbg = dbg;
-  p.timing = g_dbg_timing;
+  p.timing = g_dbg_timing;   // (cleared below for the column-split grid: the buffer is sized for one CTA per tile)
   const long long per_dir = (long long)NS * L->nrows * 3 * H * 2;
   static const int pair_on = getenv("IPN_GPF_PAIR") ? atoi(getenv("IPN_GPF_PAIR")) : 1;
-  const bool pair = pair_on && ntw % 2 == 0;
+  // column split (see the kernel's header comment): on unless IPN_GPF_CS=0; only where all the
+  // CTAs of the doubled grid are co-resident (otherwise the second wave waits and nothing is gained)
+  static const int cs_on = getenv("IPN_GPF_CS") ? atoi(getenv("IPN_GPF_CS")) : 1;
+  const bool cs = cs_on && (H / 64) % 2 == 0 && 2 * ntw * L->ndir <= 148;
+  const bool pair = !cs && pair_on && ntw % 2 == 0;
+  if (cs) p.timing = nullptr;
   char* wsp = reinterpret_cast<char*>(ws);
   bool save = false;
   for (int d = 0; d < L->ndir; ++d) {
@@ -570,13 +603,13 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
                    rows * H * 2.0 * (3 + 1 + (save ? GP_GATE_ARRAYS : 0) + (L->y ? 1 : 0)), stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(ntw, L->ndir, 1);
+    cfg.gridDim = dim3(ntw * (cs ? 2 : 1), L->ndir, 1);
     cfg.blockDim = dim3(GP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.x = (pair || cs) ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -585,11 +618,13 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[4] = {false, false, false, false};
-  if (save && pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, true>, &cfgd[0]));
-  else if (save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false>, &cfgd[1]));
-  else if (pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, true>, &cfgd[2]));
-  else IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false>, &cfgd[3]));
+  static bool cfgd[6] = {false, false, false, false, false, false};
+  if (cs && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 2>, &cfgd[4]));
+  else if (cs) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 2>, &cfgd[5]));
+  else if (save && pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, true, 1>, &cfgd[0]));
+  else if (save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 1>, &cfgd[1]));
+  else if (pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, true, 1>, &cfgd[2]));
+  else IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 1>, &cfgd[3]));
   // inter-layer dropout on the layer output
   if (L->y != nullptr && L->mask != nullptr) {
     for (int d = 0; d < L->ndir; ++d) {

@@ -58,8 +58,14 @@ constexpr int GPB_W_RING = 80 * 1024;
 constexpr int GPB_NBAR = 48;
 static inline int gpb_smem_bytes() { return GPB_A_STAGES * GP_KB_BYTES + GPB_W_RING + 4 * GP_KB_BYTES + GPB_NBAR * 8 + 16; }
 
-template <bool PAIR>
+// CS = 2 (on by default since round 2, IPN_GPB_CS=0 disables; validated on B200 with the GPU suite): COLUMN SPLIT, the
+// mirror of the forward kernel's.  The two CTAs of a cluster own the same 128-row tile and one 256-column half of dh
+// each (H = 512): half of the E phase (gate derivatives of their units) and half of every GEMM phase (N = 256 of
+// the 512 dh columns).  The K = 3H operand [dP_r, dP_z, dGn] of the GEMM phase spans both halves: each CTA
+// TMA-stores its chunks as before and signals the PEER's dg_stored barrier once the store has completed.
+template <bool PAIR, int CS>
 __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __grid_constant__ GruPersistBwd p) {
+  static_assert(CS == 1 || (CS == 2 && !PAIR), "column split uses plain (cta_group::1) MMAs");
   extern __shared__ __align__(1024) uint8_t smem[];
   const GruPersistBwdDir& D = p.d[blockIdx.y];
   const int H = p.H, KB = H >> 6, T = p.T, Bt = p.Bt;
@@ -67,10 +73,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   const int NPH = H / NH;                // columns per MMA
   const int WSTB = p.nbs * 8192;         // bytes of one W stage in this CTA
   const int WSTAGES = min(6, GPB_W_RING / WSTB);
-  const int rbase = blockIdx.x * GP_ROWS;
+  const int rbase = (CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x) * GP_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const uint32_t crank = (PAIR || CS > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t rank = PAIR ? crank : 0u;
   const bool leader = rank == 0;
+  const int h_lo = CS > 1 ? (int)crank : 0, h_hi = CS > 1 ? h_lo + 1 : NH;               // accumulator halves of this CTA
+  const int c_lo = CS > 1 ? (int)crank * (KB / CS) : 0, c_hi = c_lo + KB / CS;          // 64-unit chunks of this CTA
   const int nM = D.dh0 != nullptr ? T : T - 1;   // number of GEMM phases (the last one only feeds dh0)
 
   uint8_t* sA = smem;
@@ -87,6 +96,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   uint64_t* stg_ready = bars + 30;
   uint64_t* stg_free = bars + 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* dg_stored_odd = bars + 34; // [8] column split: the barriers of odd steps (signalled remotely: see the forward kernel)
 
   if ((ptx::smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("inpaintnet_b200: gru_persist_bwd: shared memory base not 1024-byte aligned\n");
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       for (int s = 0; s < 6; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
       for (int s = 0; s < GPB_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
       for (int k = 0; k < 8; ++k) ptx::mbar_init(&dg_stored[k], 1);
+      if (CS > 1) for (int k = 0; k < 8; ++k) ptx::mbar_init(&dg_stored_odd[k], 1);
       ptx::mbar_init(tmem_full, 1);
       ptx::mbar_init(tmem_free, PAIR ? 32 : 16);
       ptx::mbar_init(stg_ready, 16);
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();
+  if (PAIR || CS > 1) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -136,12 +147,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           ptx::bulk_prefetch_l2(D.gates + ((rt * GP_GATE_ARRAYS + a) * vpr + c * 8) * 128, 8 * 128 * 16);
         if (D.dYblk != nullptr) ptx::bulk_prefetch_l2(D.dYblk + (rt * vpr + c * 8) * 128, 8 * 128 * 16);
       };
-      for (int c = 0; c < KB; ++c) prefetch_e(0, c);
+      for (int c = c_lo; c < c_hi; ++c) prefetch_e(0, c);
       for (int it = 0; it < nM; ++it)
         for (int kb = 0; kb < KB; ++kb) {
-          prefetch_e(it + 1, kb);
+          if (kb >= c_lo && kb < c_hi) prefetch_e(it + 1, kb);
           for (int g = 0; g < 3; ++g)
-            for (int h = 0; h < NH; ++h) {
+            for (int h = h_lo; h < h_hi; ++h) {
               ptx::mbar_wait(&w_empty[stage], phase ^ 1);
               if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], (uint32_t)(WSTB * (PAIR ? 2 : 1)));
               const int nblk = h * (NPH >> 6) + (int)rank * p.nbs;
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
         for (int j = 0; j < 3 * KB; ++j) {
           wait_acc(&a_full[as], aph, tm, w_af);
           const uint64_t da0 = descA0 + (uint64_t)((as * GP_KB_BYTES) >> 4);
-          for (int h = 0; h < NH; ++h) {
+          for (int h = h_lo; h < h_hi; ++h) {
             wait_acc(&w_full[ws], wph, tm, w_wf);
             ptx::tc_fence_after();
             const uint64_t dw0 = descW0 + (uint64_t)((ws * WSTB) >> 4);
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
         const int s = T - 1 - it;
         const int tt = D.reverse ? T - 1 - s : s;
         const int grow = tt * Bt + rbase;
-        for (int c = 0; c < KB; ++c, ++i) {
+        for (int c = c_lo; c < c_hi; ++c, ++i) {
           ptx::mbar_wait(stg_ready, i & 1);
 #pragma unroll
           for (int g = 0; g < 3; ++g) ptx::tma_store_2d(&D.tmDP, sStg + g * GP_KB_BYTES, g * H + c * 64, grow);
@@ -220,7 +231,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           ptx::bulk_wait_read0();
           ptx::mbar_arrive(stg_free);
           ptx::bulk_wait0();
-          ptx::mbar_arrive(&dg_stored[c]);
+          if (CS > 1) {   // the peer streams these dP / dGn chunks as k-blocks of its GEMM phase
+            uint64_t* ds = (it & 1) ? &dg_stored_odd[c] : &dg_stored[c];
+            ptx::mbar_arrive(ds);
+            __threadfence();
+            ptx::mbar_arrive_remote_release(ds, crank ^ 1u);
+          } else {
+            ptx::mbar_arrive(&dg_stored[c]);
+          }
         }
       }
     }
@@ -234,7 +252,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
         const int tt = D.reverse ? T - 1 - s : s;
         const int grow = tt * Bt + rbase;
         for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(&dg_stored[kb], it & 1);
+          if (CS > 1) {   // barrier set it & 1, phase (it >> 1) & 1; the peer's chunks at cluster scope
+            uint64_t* ds = (it & 1) ? &dg_stored_odd[kb] : &dg_stored[kb];
+            if (kb < c_lo || kb >= c_hi) ptx::mbar_wait_cluster(ds, (it >> 1) & 1);
+            else ptx::mbar_wait(ds, (it >> 1) & 1);
+          } else {
+            ptx::mbar_wait(&dg_stored[kb], it & 1);
+          }
           ptx::fence_proxy_async_all();
           for (int g = 0; g < 3; ++g) {
             ptx::mbar_wait(&a_empty[as], aph ^ 1);
@@ -265,7 +289,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       const int s = T - 1 - it;
       const int tt = D.reverse ? T - 1 - s : s;
       const long long rt = ((long long)tt * Bt + rbase) >> 7;
-      for (int c = 0; c < KB; ++c, ++i) {
+      for (int c = c_lo; c < c_hi; ++c, ++i) {
         const uint4* gp = D.gates + ((rt * GP_GATE_ARRAYS) * vpr + c * 8 + sub * 2) * 128 + row;
         const uint4* yp = D.dYblk != nullptr ? D.dYblk + (rt * vpr + c * 8 + sub * 2) * 128 + row : nullptr;
         const int u0 = c * 64 + sub * 16;
@@ -277,7 +301,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           for (int a = 0; a < 5; ++a) gv[v][a] = ldg_stream(gp + a * astride + v * 128);
           yv[v] = yp != nullptr ? ldg_stream(yp + v * 128) : make_uint4(0, 0, 0, 0);
         }
-        if (c == 0 && it > 0) {   // the first chunk's loads are in flight while the GEMM phase finishes
+        if (c == c_lo && it > 0) {   // the first chunk's loads are in flight while the GEMM phase finishes
           ptx::mbar_wait(tmem_full, (it - 1) & 1);
           ptx::tc_fence_after();
         }
@@ -340,7 +364,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       // gradient wrt the initial state: accumulator after the last GEMM phase
       ptx::mbar_wait(tmem_full, (T - 1) & 1);
       ptx::tc_fence_after();
-      for (int c = 0; c < KB; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         const int u0 = c * 64 + sub * 16;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
@@ -368,7 +392,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();
+  if (PAIR || CS > 1) ptx::cluster_sync_all();
   if (warp == 1) {
     ptx::tc_fence_after();
     if (PAIR) ptx::tmem_dealloc_pair<512>(tmem_base);
@@ -416,7 +440,11 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
   p.timing = g_dbg_timing;
   const int NH = H > 256 ? 2 : 1, NPH = H / NH;
   static const int pair_on = getenv("IPN_GPB_PAIR") ? atoi(getenv("IPN_GPB_PAIR")) : 1;
-  const bool pair = pair_on && (Bt / GP_ROWS) % 2 == 0 && NPH % 128 == 0;
+  // column split (kernel header comment): on unless IPN_GPB_CS=0
+  static const int cs_on = getenv("IPN_GPB_CS") ? atoi(getenv("IPN_GPB_CS")) : 1;
+  const bool cs = cs_on && NH == 2 && 2 * (Bt / GP_ROWS) * L->ndir <= 148;
+  const bool pair = !cs && pair_on && (Bt / GP_ROWS) % 2 == 0 && NPH % 128 == 0;
+  if (cs) p.timing = nullptr;   // the diagnostics buffer is sized for one CTA per tile
   p.nbs = pair ? NPH / 128 : NPH / 64;
   const long long per_dir = (long long)T * Bt * H * 2;
   char* wsp = reinterpret_cast<char*>(ws);
@@ -455,13 +483,13 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
                    rows * H * 2.0 * (GP_GATE_ARRAYS + 4 + (L->dY ? 1 : 0)), stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(Bt / GP_ROWS, L->ndir, 1);
+    cfg.gridDim = dim3(Bt / GP_ROWS * (cs ? 2 : 1), L->ndir, 1);
     cfg.blockDim = dim3(GP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = gpb_smem_bytes();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.x = (pair || cs) ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -470,9 +498,10 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[2] = {false, false};
-  if (pair) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<true>, &cfgd[0]));
-  else IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false>, &cfgd[1]));
+  static bool cfgd[3] = {false, false, false};
+  if (cs) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false, 2>, &cfgd[2]));
+  else if (pair) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<true, 1>, &cfgd[0]));
+  else IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false, 1>, &cfgd[1]));
   return IPN_OK;
 }
 

@@ -44,6 +44,8 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
   IPN_REQUIRE(0 <= s_begin && s_begin < s_end && s_end <= T, IPN_ERR_ARG, "lstm_layer_fwd: bad step range");
   IPN_REQUIRE(!L->table || L->tok_scalar, IPN_ERR_ARG, "lstm_layer_fwd: table without token");
   if (L->P_blocked) return lstm_persist_fwd(L, s_begin, s_end, stream);
+  IPN_REQUIRE(!L->gates_blocked || (ipn_lstm_persist_eligible(L->core, L->act_dt, L->B, L->H) && L->gates != nullptr), IPN_ERR_ARG,
+              "lstm_layer_fwd: gates_blocked needs a shape the persistent kernels accept (bf16, H 128/256, B %% 128 == 0)");
   auto fill_epi = [&](EpiLstmFwd::Params& e, int s) {
     e.H = H; e.act_dt = dt; e.trow = s * B;
     e.P = L->P; e.ldP = L->ldP; e.b_hh = L->b_hh;
@@ -53,6 +55,7 @@ extern "C" int ipn_lstm_layer_fwd(const IpnLstmLayer* L, void* stream_) {
     e.gates = L->gates; e.y = L->y; e.ld_y = L->ld_y; e.y_col0 = L->y_col0;
     e.ytrow = (L->y_reverse_time ? (T - 1 - s) : s) * B;
     e.table = L->table; e.ld_table = L->ld_table; e.tok_scalar = L->tok_scalar;
+    e.gates_blocked = L->gates_blocked;
   };
   if (L->core == IPN_CORE_SIMT) {
     SimtBatch<EpiLstmFwd> b;

@@ -38,6 +38,7 @@ struct LstmPersistFwd {
   int T, B;
   int s_begin, s_end;
   int has_y, y_col0, y_reverse_time;
+  unsigned long long* timing;    // per-CTA cycle counters (ipn_dbg_set_timing_buffer), normally null
 };
 
 struct LstmPersistBwd {
@@ -47,6 +48,7 @@ struct LstmPersistBwd {
   const uint4* gates;            // blocked [T*B, 5, H]
   int T, B;
   int y_col0, y_reverse_time;
+  unsigned long long* timing;
 };
 
 __device__ __forceinline__ void st_cluster_u4(uint32_t caddr, const uint4& u) { ptx::st_cluster_v4(caddr, u.x, u.y, u.z, u.w); }
@@ -121,14 +123,20 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
       const uint64_t descA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024);
       const uint64_t descW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024);
       ptx::mbar_wait(w_full, 0);
+      const bool tm = p.timing != nullptr;
+      long long w_own = 0, w_peer = 0;
+      const long long t_begin = clock64();
       for (int t = 0; t < NS; ++t) {
         if (t == 0) {
           ptx::mbar_wait(a0_full, 0);
         } else {
           // own k-block first: its arrival also says that this CTA's epilogue has read the accumulator of step t-1
+          const long long c0 = tm ? clock64() : 0;
           ptx::mbar_wait_cluster(&a_ready[rank], (t - 1) & 1);
+          const long long c1 = tm ? clock64() : 0;
           for (int kb = 0; kb < NC; ++kb)
             if (kb != (int)rank) ptx::mbar_wait_cluster(&a_ready[kb], (t - 1) & 1);
+          if (tm) { w_own += c1 - c0; w_peer += clock64() - c1; }
         }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -141,6 +149,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
           ptx::umma_commit_multicast(mma_all, (uint16_t)((1u << NC) - 1u));
         }
         __syncwarp();
+      }
+      if (tm && lane == 0) {
+        unsigned long long* o = p.timing + (long long)blockIdx.x * 16;
+        o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_own; o[2] = w_peer;
       }
     } else if (warp == 2) {
       // ===================== store warp: own k-block of h_t -> hseq slot (+ y) =====================
@@ -181,6 +193,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
       ptx::bulk_prefetch_l2(p.Pblk + ((rtp * 4 + sub) * VPR + rank * 8) * 128, 8 * 128 * 16);
     };
     for (int t = 0; t < 4; ++t) prefetch(t);
+    const bool tm = p.timing != nullptr && threadIdx.x == 128;
+    long long w_mma = 0, w_st = 0, w_work = 0, w_sig = 0;
+    const long long te0 = clock64();
     float c[2][8];
     {
       const float4* cp = reinterpret_cast<const float4*>(p.cseq + ((long long)p.s_begin * B + rbase + row) * H + u0);
@@ -202,9 +217,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
       for (int g = 0; g < 4; ++g)
 #pragma unroll
         for (int v = 0; v < 2; ++v) pv[g][v] = ldg_stream(pb + (g * VPR + v) * 128);
+      const long long c0 = tm ? clock64() : 0;
       ptx::mbar_wait(mma_all, t & 1);
       ptx::tc_fence_after();
+      const long long c1 = tm ? clock64() : 0;
       if (t > 0) ptx::mbar_wait(st_free, (t - 1) & 1);
+      const long long c2 = tm ? clock64() : 0;
       uint4* gp = SAVE ? p.gates + ((rt * LP_ARR) * VPR + (u0 >> 3)) * 128 + row : nullptr;
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
@@ -241,6 +259,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
           stg_stream(gp + (4 * VPR + v) * 128, pack8(c[v]));
         }
       }
+      const long long c3 = tm ? clock64() : 0;
       ptx::tc_fence_before();
       ptx::fence_proxy_async_all();   // h_t slices (local + remote shared memory) -> visible to the MMAs / the TMA store
       __syncwarp();
@@ -252,6 +271,11 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
             if (pr != (int)rank) ptx::mbar_arrive_cluster(bar_remote[pr]);
         }
       }
+      if (tm) { w_mma += c1 - c0; w_st += c2 - c1; w_work += c3 - c2; w_sig += clock64() - c3; }
+    }
+    if (tm) {
+      unsigned long long* o = p.timing + (long long)blockIdx.x * 16;
+      o[4] = (unsigned long long)(clock64() - te0); o[5] = w_mma; o[6] = w_st; o[7] = w_work; o[8] = w_sig;
     }
     {   // cell state after the last processed step
       float4* cp = reinterpret_cast<float4*>(p.cseq + ((long long)p.s_end * B + rbase + row) * H + u0);
@@ -414,6 +438,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
     const uint32_t slot_at_peer = (rank + (uint32_t)NC - peer - 1u) % (uint32_t)NC;
     const uint32_t send_base = sender ? ptx::mapa(sA_u + slot_at_peer * LP_KB, peer) : 0u;
     const uint32_t send_bar = sender ? ptx::mapa(ptx::smem_u32(recv_full), peer) : 0u;
+    const bool tm = p.timing != nullptr && threadIdx.x == 128;
+    long long w_dy = 0, w_recv = 0, w_e = 0, w_mma = 0, w_s = 0;
+    const long long te0 = clock64();
     float dc[2][8], cc[2][8];   // carried dL/dc and the cell state c_s of the step being differentiated
 #pragma unroll
     for (int v = 0; v < 2; ++v)
@@ -442,7 +469,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
         }
       }
       const int st = it & 1;
+      const long long c0 = tm ? clock64() : 0;
       ptx::mbar_wait(&dy_full[st], (it >> 1) & 1);
+      const long long c1 = tm ? clock64() : 0;
       float dh[2][8];
 #pragma unroll
       for (int v = 0; v < 2; ++v)
@@ -451,8 +480,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
       if (lane == 0) ptx::mbar_arrive(&dy_empty[st]);
       if (it > 0) {
         // recurrent part: own partial sum (accumulator) + the partial sums the peers sent (bf16, swizzled rows)
+        const long long r0 = tm ? clock64() : 0;
         ptx::mbar_wait_cluster(recv_full, (it - 1) & 1);
         ptx::tc_fence_after();
+        if (tm) w_recv += clock64() - r0;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           float own[8];
@@ -497,10 +528,13 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
       ptx::fence_proxy_async();   // dG tile -> visible to the MMAs and the dP TMA stores
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(dg_ready);
+      const long long c2 = tm ? clock64() : 0;
+      if (tm) { w_dy += c1 - c0; w_e += c2 - c1; }
       if (it < nM) {
         // ---- after the GEMM phase: send the partial sums of the peers' columns (reduce-scatter through DSMEM)
         ptx::mbar_wait(mma_all, it & 1);
         ptx::tc_fence_after();
+        const long long c3 = tm ? clock64() : 0;
         if (sender) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -513,7 +547,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(send_bar);
         }
+        if (tm) { w_mma += c3 - c2; w_s += clock64() - c3; }
       }
+    }
+    if (tm) {
+      unsigned long long* o = p.timing + (long long)blockIdx.x * 16;
+      o[4] = (unsigned long long)(clock64() - te0); o[5] = w_dy; o[6] = w_recv; o[7] = w_e; o[8] = w_mma; o[9] = w_s;
     }
   }
   ptx::tc_fence_before();
@@ -576,6 +615,7 @@ int lstm_persist_fwd(const IpnLstmLayer* L, int s_begin, int s_end, cudaStream_t
   p.cseq = L->cseq;
   p.T = T; p.B = B; p.s_begin = s_begin; p.s_end = s_end;
   p.y_col0 = L->y_col0; p.y_reverse_time = L->y_reverse_time;
+  p.timing = g_dbg_timing;
   const bool save = L->gates != nullptr;
   const double rows = (double)(s_end - s_begin) * B;
   ProfScope prof("lstm_layer_fwd_persist", 2.0 * rows * 4.0 * H * H, rows * H * 2.0 * (4 + 1 + (save ? LP_ARR : 0) + (p.has_y ? 1 : 0)), stream);
@@ -602,6 +642,7 @@ int lstm_persist_bwd(const IpnLstmLayerBwd* L, cudaStream_t stream) {
   p.gates = reinterpret_cast<const uint4*>(L->gates);
   p.T = T; p.B = B;
   p.y_col0 = L->y_col0; p.y_reverse_time = L->y_reverse_time;
+  p.timing = g_dbg_timing;
   const double rows = (double)T * B;
   ProfScope prof("lstm_layer_bwd_persist", 2.0 * rows * 4.0 * H * H, rows * H * 2.0 * (LP_ARR + 1 + 4), stream);
   static bool cfgd[2] = {false, false};

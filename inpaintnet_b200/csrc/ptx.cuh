@@ -205,6 +205,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// cluster-scope variants for barriers that a PEER CTA signals after writing global memory this CTA is about to read
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
 // TMA load issued by either CTA of a pair; the bytes are accounted on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0, int crd1) {
   asm volatile(

@@ -172,9 +172,9 @@ def lstm_inproj_blocked(X, ldx, K, w_ih, ldw, rows, b_ih, b_hh, H, out, X2=0, ld
 
 
 def lstm_layer_fwd(prec, T, B, H, w_hh, b_hh, P, ldP, hseq, cseq, gates=0, y=0, ld_y=0, y_col0=0, y_reverse_time=0,
-                   s_begin=0, s_end=0, table=0, ld_table=0, tok_scalar=0, P_blocked=0):
+                   s_begin=0, s_end=0, table=0, ld_table=0, tok_scalar=0, P_blocked=0, gates_blocked=0):
     p = L.LstmLayer()
-    p.P_blocked = P_blocked
+    p.P_blocked, p.gates_blocked = P_blocked, gates_blocked
     p.y_reverse_time, p.s_begin, p.s_end = y_reverse_time, s_begin, s_end
     p.table, p.ld_table, p.tok_scalar = table or None, ld_table, tok_scalar or None
     p.core, p.act_dt, p.T, p.B, p.H = prec.core, prec.act, T, B, H
