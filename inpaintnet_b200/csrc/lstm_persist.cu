@@ -57,7 +57,7 @@ __device__ __forceinline__ void st_cluster_u4(uint32_t caddr, const uint4& u) { 
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int NC>
-static inline int lpf_smem_bytes() { return NC * LP_WKB + NC * LP_KB + 16 * 8 + 16; }
+static inline int lpf_smem_bytes() { return NC * LP_WKB + NC * LP_KB + 16 * 8 + 16; }   // 9 barriers + the TMEM slot
 
 template <int NC, bool SAVE>
 __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const __grid_constant__ LstmPersistFwd p) {
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
   uint64_t* a_ready = bars + 2;     // [NC] k-block kb of h_t written by the 16 epilogue warps of CTA kb
   uint64_t* mma_all = bars + 6;     // the MMAs of this step are complete in ALL CTAs of the cluster (multicast commits)
   uint64_t* st_free = bars + 7;     // the TMA store of the previous h_t has read this CTA's k-block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* tmem_full = bars + 8;   // THIS CTA's MMAs of the step are complete (local commit: no cluster round trip)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   if ((ptx::smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("inpaintnet_b200: lstm_persist_fwd: shared memory base not 1024-byte aligned\n");
@@ -88,9 +89,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
     if (lane == 0) {
       ptx::mbar_init(w_full, 1);
       ptx::mbar_init(a0_full, 1);
-      for (int k = 0; k < NC; ++k) ptx::mbar_init(&a_ready[k], 16);
+      // own k-block: the 16 epilogue warps arrive; a peer's k-block: one local arrive.expect_tx + the bytes of the
+      // peer's bulk copy (complete_tx)
+      for (int k = 0; k < NC; ++k) ptx::mbar_init(&a_ready[k], k == (int)rank ? 16 : 1);
       ptx::mbar_init(mma_all, NC);
       ptx::mbar_init(st_free, 1);
+      ptx::mbar_init(tmem_full, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -140,13 +144,20 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
         }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
+          // arm the peers' k-blocks of h_t BEFORE the commit below: a peer sends only after mma_all of this step
+          if (t + 1 < NS) {
+#pragma unroll
+            for (int kb = 0; kb < NC; ++kb)
+              if (kb != (int)rank) ptx::mbar_arrive_expect_tx(&a_ready[kb], LP_KB);
+          }
 #pragma unroll
           for (int kb = 0; kb < NC; ++kb)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               ptx::umma_bf16(tmem_base, descA0 + (uint64_t)((kb * LP_KB) >> 4) + (uint64_t)(kk * 2),
                              descW0 + (uint64_t)((kb * LP_WKB) >> 4) + (uint64_t)(kk * 2), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-          ptx::umma_commit_multicast(mma_all, (uint16_t)((1u << NC) - 1u));
+          ptx::umma_commit(tmem_full);                                           // own epilogue may start
+          ptx::umma_commit_multicast(mma_all, (uint16_t)((1u << NC) - 1u));     // every A tile of the cluster may be overwritten
         }
         __syncwarp();
       }
@@ -157,9 +168,25 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
     } else if (warp == 2) {
       // ===================== store warp: own k-block of h_t -> hseq slot (+ y) =====================
       if (lane == 0) {
+        const uint32_t src = ptx::smem_u32(sA) + rank * LP_KB;
+        uint32_t dst[NC], dbar[NC];
+#pragma unroll
+        for (int pr = 0; pr < NC; ++pr) {
+          dst[pr] = ptx::mapa(src, (uint32_t)pr);
+          dbar[pr] = ptx::mapa(ptx::smem_u32(&a_ready[rank]), (uint32_t)pr);
+        }
         for (int t = 0; t < NS; ++t) {
           const int s = p.s_begin + t;
           ptx::mbar_wait(&a_ready[rank], t & 1);
+          // the exchange: this CTA's 16 KB slice of h_t goes to k-block `rank` of every peer's A tile as ONE bulk
+          // copy per peer through distributed shared memory (completes on the peer's a_ready[rank]); the peers' A
+          // tiles are free once the MMAs of the whole cluster are done (long since: the epilogue ran in between)
+          ptx::mbar_wait(mma_all, t & 1);
+          if (t + 1 < NS) {
+#pragma unroll
+            for (int pr = 0; pr < NC; ++pr)
+              if (pr != (int)rank) ptx::bulk_copy_s2s_cluster(dst[pr], src, LP_KB, dbar[pr]);
+          }
           ptx::tma_store_2d(&p.tmH, sA + rank * LP_KB, (int)rank * 64, (s + 1) * B + rbase);
           if (p.has_y) ptx::tma_store_2d(&p.tmY, sA + rank * LP_KB, p.y_col0 + (int)rank * 64, (p.y_reverse_time ? T - 1 - s : s) * B + rbase);
           ptx::bulk_commit();
@@ -179,12 +206,6 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
     const uint32_t sA_u = ptx::smem_u32(sA) + rank * LP_KB;   // this CTA's k-block inside an A tile
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 16);
-    uint32_t a_remote[NC], bar_remote[NC];
-#pragma unroll
-    for (int pr = 0; pr < NC; ++pr) {
-      a_remote[pr] = ptx::mapa(sA_u, (uint32_t)pr);
-      bar_remote[pr] = ptx::mapa(ptx::smem_u32(&a_ready[rank]), (uint32_t)pr);
-    }
     // the input-projection tiles are pulled from HBM into L2 four steps ahead (one gate array per sub-chunk warp group);
     // issued from the epilogue, which is in lockstep with the chain by construction
     auto prefetch = [&](int t) {
@@ -209,7 +230,6 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
     for (int t = 0; t < NS; ++t) {
       const int s = p.s_begin + t;
       const long long rt = ((long long)s * B + rbase) >> 7;
-      const bool last = t + 1 == NS;
       prefetch(t + 4);
       const uint4* pb = p.Pblk + ((rt * 4) * VPR + (u0 >> 3)) * 128 + row;
       uint4 pv[4][2];
@@ -218,12 +238,13 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
 #pragma unroll
         for (int v = 0; v < 2; ++v) pv[g][v] = ldg_stream(pb + (g * VPR + v) * 128);
       const long long c0 = tm ? clock64() : 0;
-      ptx::mbar_wait(mma_all, t & 1);
+      ptx::mbar_wait(tmem_full, t & 1);   // own MMAs only: the epilogue writes nothing outside this CTA
       ptx::tc_fence_after();
       const long long c1 = tm ? clock64() : 0;
       if (t > 0) ptx::mbar_wait(st_free, (t - 1) & 1);
       const long long c2 = tm ? clock64() : 0;
       uint4* gp = SAVE ? p.gates + ((rt * LP_ARR) * VPR + (u0 >> 3)) * 128 + row : nullptr;
+      uint4 gsave[2][LP_ARR];
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
         float acc[4][8];
@@ -243,33 +264,23 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_fwd_kernel(const _
           gi[k] = i_; gf[k] = f_; gg[k] = g_; go[k] = o_;
           hh[k] = o_ * tanh_fast(cn);
         }
-        const uint4 hv = pack8(hh);
-        const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(sub * 2 + v)) ^ sw) << 4);
-        st_shared_v4(sA_u + off, hv);
-        if (!last) {
-#pragma unroll
-          for (int pr = 0; pr < NC; ++pr)
-            if (pr != (int)rank) st_cluster_u4(a_remote[pr] + off, hv);
-        }
+        st_shared_v4(sA_u + (uint32_t)row * 128u + ((((uint32_t)(sub * 2 + v)) ^ sw) << 4), pack8(hh));
         if (SAVE) {
-          stg_stream(gp + (0 * VPR + v) * 128, pack8(gi));
-          stg_stream(gp + (1 * VPR + v) * 128, pack8(gf));
-          stg_stream(gp + (2 * VPR + v) * 128, pack8(gg));
-          stg_stream(gp + (3 * VPR + v) * 128, pack8(go));
-          stg_stream(gp + (4 * VPR + v) * 128, pack8(c[v]));
+          gsave[v][0] = pack8(gi); gsave[v][1] = pack8(gf); gsave[v][2] = pack8(gg); gsave[v][3] = pack8(go);
+          gsave[v][4] = pack8(c[v]);
         }
       }
       const long long c3 = tm ? clock64() : 0;
       ptx::tc_fence_before();
-      ptx::fence_proxy_async_all();   // h_t slices (local + remote shared memory) -> visible to the MMAs / the TMA store
+      ptx::fence_proxy_async();   // own h_t slice (shared::cta) -> visible to the bulk copies / the TMA store / the MMAs
       __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&a_ready[rank]);
-        if (!last) {
+      if (lane == 0) ptx::mbar_arrive(&a_ready[rank]);
+      // the saved state goes out AFTER the signal: nothing on the serial chain waits for these global stores
+      if (SAVE) {
 #pragma unroll
-          for (int pr = 0; pr < NC; ++pr)
-            if (pr != (int)rank) ptx::mbar_arrive_cluster(bar_remote[pr]);
-        }
+        for (int v = 0; v < 2; ++v)
+#pragma unroll
+          for (int a = 0; a < LP_ARR; ++a) stg_stream(gp + (a * VPR + v) * 128, gsave[v][a]);
       }
       if (tm) { w_mma += c1 - c0; w_st += c2 - c1; w_work += c3 - c2; w_sig += clock64() - c3; }
     }
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
       ptx::mbar_init(dg_ready, 16);
       ptx::mbar_init(dp_read, 1);
       ptx::mbar_init(mma_all, NC);
-      ptx::mbar_init(recv_full, (NC - 1) * 4);
+      ptx::mbar_init(recv_full, (NC - 1) * 16);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -431,13 +442,15 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
     const uint32_t sA_u = ptx::smem_u32(sA), sDY_u = ptx::smem_u32(sDY);
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    // sender role between GEMM phases: warps with sub < NC-1 send the partial columns of peer (rank + 1 + sub) % NC
-    const bool sender = sub < NC - 1;
-    const uint32_t peer = (rank + 1u + (uint32_t)sub) % (uint32_t)NC;
-    // receive slot of `rank` inside peer's A tile: (rank - peer - 1) mod NC  (slots 0 .. NC-2)
-    const uint32_t slot_at_peer = (rank + (uint32_t)NC - peer - 1u) % (uint32_t)NC;
-    const uint32_t send_base = sender ? ptx::mapa(sA_u + slot_at_peer * LP_KB, peer) : 0u;
-    const uint32_t send_bar = sender ? ptx::mapa(ptx::smem_u32(recv_full), peer) : 0u;
+    // between GEMM phases every thread sends, to each peer, the partial sums of ITS row for the 16 columns that the
+    // peer's thread (row, sub) owns: peer (rank + pr) % NC receives them in slot NC - 1 - pr of its A tile
+    uint32_t send_base[NC], send_bar[NC];
+#pragma unroll
+    for (int pr = 1; pr < NC; ++pr) {
+      const uint32_t peer = (rank + (uint32_t)pr) % (uint32_t)NC;
+      send_base[pr] = ptx::mapa(sA_u + (uint32_t)(NC - 1 - pr) * LP_KB, peer);
+      send_bar[pr] = ptx::mapa(ptx::smem_u32(recv_full), peer);
+    }
     const bool tm = p.timing != nullptr && threadIdx.x == 128;
     long long w_dy = 0, w_recv = 0, w_e = 0, w_mma = 0, w_s = 0;
     const long long te0 = clock64();
@@ -535,17 +548,21 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
         ptx::mbar_wait(mma_all, it & 1);
         ptx::tc_fence_after();
         const long long c3 = tm ? clock64() : 0;
-        if (sender) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float part[8];
-            ptx::tmem_ld8(tlane + (uint32_t)(peer * 64 + j * 8), part);
-            ptx::tmem_ld_wait();
-            st_cluster_u4(send_base + (uint32_t)row * 128u + ((((uint32_t)j) ^ sw) << 4), pack8(part));
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(send_bar);
+        for (int pr = 1; pr < NC; ++pr) {
+          const uint32_t peer = (rank + (uint32_t)pr) % (uint32_t)NC;
+          float part[16];
+          ptx::tmem_ld16(tlane + (uint32_t)(peer * 64 + sub * 16), part);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+            st_cluster_u4(send_base[pr] + (uint32_t)row * 128u + ((((uint32_t)(sub * 2 + v)) ^ sw) << 4), pack8(part + 8 * v));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int pr = 1; pr < NC; ++pr) ptx::mbar_arrive_cluster(send_bar[pr]);
         }
         if (tm) { w_mma += c3 - c2; w_s += clock64() - c3; }
       }

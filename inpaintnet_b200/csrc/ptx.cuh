@@ -301,6 +301,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// bulk copy from this CTA's shared memory into the shared memory of another CTA of the cluster (dst / bar: shared::cluster
+// addresses from mapa); the bytes are accounted (complete_tx) on the DESTINATION CTA's mbarrier
+__device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_caddr, uint32_t src_saddr, uint32_t bytes, uint32_t bar_caddr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_caddr), "r"(src_saddr), "r"(bytes), "r"(bar_caddr)
+               : "memory");
+}
 // arrives on the mbarrier at this offset in every CTA of `cta_mask` once all MMAs issued so far by this thread are done
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

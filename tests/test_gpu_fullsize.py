@@ -255,3 +255,33 @@ def test_arnn_free_running_forward_full_size(prec, B):
         kk = min(k + 1, 384)                                # the first differing tick still saw identical inputs
         assert rel_err(logits[rows, :kk], ref[:, :kk]) < 3e-2, k
         print(f"arnn free-running [bf16]: fed-back tokens agree with the fp32 oracle on the first {k}/384 ticks")
+
+
+def test_arnn_free_running_backward_uses_persistent_kernel_on_blocked_gates():
+    """No teacher forcing, bf16, H = 256: the generation stack runs tick by tick (token feedback) but saves its state
+    in the persistent kernels' blocked layout, so the whole backward pass runs the persistent cluster kernels; every
+    gradient against the oracle's autograd of the same free-running forward (arnn_model.py:190-259)."""
+    from inpaintnet_b200 import functional as Fn
+    V, B = 64, 256
+    m = _arnn(V, "bf16")
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.train()
+    m.teacher_forcing_prob = -1.0
+    score, md, cl, gap = _arnn_inputs(B, V, 53)
+    m.zero_grad()
+    weights, _ = m(score.to(DEV), md.to(DEV), cl.to(DEV), train=True)
+    targets = score[:, 0, gap]
+    loss, _ = Fn.fused_ce_kl(weights[0], targets.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    sdr = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ref, fed = O.arnn_forward_no_tf(sdr, score, md, cl)
+    if not torch.equal(weights[0][0].argmax(1).cpu(), ref[0, gap].argmax(1)):
+        pytest.skip("bf16 token feedback diverged from the fp32 oracle after a near-tie: gradients are not comparable")
+    assert rel_err(weights[0].detach().cpu(), ref.detach()[:, gap]) < 3e-2
+    O.mean_crossentropy_loss(ref[:, gap], targets).backward()
+    errs = grad_errs(m.named_parameters(), {k: v.grad for k, v in sdr.items()})
+    print(f"arnn free-running backward [bf16, blocked gates]: max grad err {max(errs.values()):.3e} ({max(errs, key=errs.get)})")
+    # measured: everything < 0.15 except the single-row voice-index embedding (0.16: a sum of 98304 bf16-rounded rows)
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < 0.2}
+    assert not bad, bad
