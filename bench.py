@@ -141,6 +141,10 @@ def run_reference_arm(args):
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     extra = json.loads(args.cpu_extra) if args.cpu_extra else {}
+    if not extra.get("cuda"):
+        # the CPU arm: the reference's helpers move tensors to the GPU whenever one is visible (utils/helpers.py:5-26)
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
+        torch.cuda.is_available = lambda: False
     r = time_cpu(args.workload, args.cpu_size, steps, warmup, args.cpu_budget_s, extra)
     metric, unit = CPU_METRIC[args.workload]
     if r is None:
@@ -159,6 +163,9 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if extra.get("cuda"):
+        line["config"]["workload"] = line["config"]["workload"].replace("CPU bounded sample", "reference's own torch/cuDNN GPU path")
+        line["dtype"] = "f32 (cuDNN)"
     print(json.dumps(line))
 
 
@@ -166,7 +173,8 @@ def cpu_baseline_subprocess(workload, steps, warmup, size=0, extra=None, budget_
     """Runs the CPU arm in its own interpreter (its own thread pool, no module-name clash with the drop-in packages)."""
     env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE",
                                                             "LOCAL_RANK", "CUDA_VISIBLE_DEVICES")}
-    env["CUDA_VISIBLE_DEVICES"] = ""
+    if not (extra or {}).get("cuda"):
+        env["CUDA_VISIBLE_DEVICES"] = ""
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", str(steps),
            "--warmup", str(warmup), "--cpu-size", str(size), "--cpu-budget-s", str(budget_s)]
     if extra:
@@ -652,9 +660,12 @@ def main():
             c["floor_note"] = ("encoder layer step at B=4096, both directions: 12.9 GFLOP -> %.1f us at the tensor peak; 84 MB "
                                "algorithmic bytes -> %.1f us at the HBM peak" % (12.9e9 / (cx.tf_peak * 1e12) * 1e6,
                                                                                 84e6 / (cx.hbm_peak * 1e9) * 1e6))
-        cpu = cpu_inp = cpu_lat = cpu_arnn = None
+        cpu = ref_gpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_subprocess("mvae_train", 3, 1, size=1024)
+            # context only (SURVEY.md section 2.2 "the bar"): the UNMODIFIED reference on this same B200 through torch's
+            # cuDNN GRU path, fp32, at the full 4096-measure batch, with the reference's own ~50 host syncs per step
+            ref_gpu = cpu_baseline_subprocess("mvae_train", 5, 2, size=B, extra={"cuda": True})
             if inpaint is not None:
                 inpaint["cpu_baseline"] = cpu_baseline_subprocess("inpaint", 2, 1, size=256)
             if latent is not None:
@@ -679,6 +690,7 @@ def main():
             "roofline": roofline,
             "roofline_critical_path": crit,
             "cpu_baseline": cpu,
+            "reference_on_this_gpu": ref_gpu,
             "modes": mv["modes"],
             "kernels": cx.kernel_table(kernels),
             "inpaint": inpaint,

@@ -47,21 +47,29 @@ def _metadata(B, T=384):
 
 
 class MvaeTrain:
-    """MeasureVAE train step: MeasureVAE/vae_trainer.py:16-40 + utils/trainer.py:136-156 (config 1 / 2 on the CPU)."""
+    """MeasureVAE train step: MeasureVAE/vae_trainer.py:16-40 + utils/trainer.py:136-156 (config 1 / 2 on the CPU).
+    cuda=True: the same unmodified code on the GPU the way train_measure_vae.py:105 runs it (model.cuda(); torch's
+    cuDNN GRU; the reference's own per-step host syncs included) -- context only, SURVEY.md section 2.2."""
     unit = "measures/s"
 
-    def __init__(self, measures, seed=0):
+    def __init__(self, measures, seed=0, cuda=False):
         from oracle.ref_import import load_reference, FakeDataset
         R = load_reference()
         torch.manual_seed(seed)
         random.seed(seed)
         ds = FakeDataset(V)
         self.model = R.MeasureVAE(ds)                       # reference defaults (E 10, H 512, L 2, Z 256, p 0.5)
+        if cuda:
+            self.model.cuda()
         self.trainer = R.VAETrainer(ds, self.model, lr=1e-4)
         self.model.train()
         self.tokens = torch.randint(0, V, (measures, 24))
+        if cuda:
+            self.tokens = self.tokens.cuda()
+        self.cuda = cuda
         self.units = measures
-        self.what = f"{measures} measures (unmodified reference MeasureVAE + VAETrainer: fwd, loss, backward, Adam; train mode)"
+        self.what = (f"{measures} measures (unmodified reference MeasureVAE + VAETrainer: fwd, loss, backward, Adam; train mode"
+                     + ("; on the GPU: torch cuDNN GRU path, fp32" if cuda else "") + ")")
 
     def step(self):
         tr = self.trainer
@@ -175,7 +183,17 @@ def run(workload, size, steps, warmup, **kw):
     """Times `steps` steps after `warmup`; returns dict(value, unit, cores, kind, sample, s_per_step)."""
     cores = _threads()
     w = WORKLOADS[workload](size, **kw)
-    per = _time_steps(w.step, steps, warmup)
+    on_gpu = bool(getattr(w, "cuda", False))
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    for _ in range(warmup):
+        w.step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.step()
+    sync()
+    per = (time.perf_counter() - t0) / max(1, steps)
+    where = f"torch {torch.__version__} " + (f"CUDA ({torch.cuda.get_device_name(0)}, cuDNN {torch.backends.cudnn.version()})" if on_gpu else "CPU")
     return dict(value=w.units / per, unit=w.unit, cores=cores, kind="reference",
-                sample=f"{steps} steps of {w.what}, after {warmup} warm-up, fp32, {per:.2f} s/step, torch {torch.__version__} CPU",
+                sample=f"{steps} steps of {w.what}, after {warmup} warm-up, fp32, {per * 1e3:.1f} ms/step, {where}",
                 s_per_step=per, units_per_step=w.units)
