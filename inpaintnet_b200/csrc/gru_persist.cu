@@ -129,7 +129,7 @@ static inline int gpf_smem_bytes(int H) {
 // h_stored[chunk] barrier once the store has completed; the A loaders reload all k-blocks from L2 as before.
 template <bool SAVE, bool PAIR, int CS>
 __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __grid_constant__ GruPersistFwd p) {
-  static_assert(CS == 1 || (CS == 2 && !PAIR), "column split uses plain (cta_group::1) MMAs");
+  static_assert(CS == 1 || ((CS == 2 || CS == 4) && !PAIR), "column split uses plain (cta_group::1) MMAs");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int WST_BYTES = PAIR ? GPF_W_BYTES / 2 : GPF_W_BYTES;  // per-CTA bytes of one W stage
   constexpr int WSTAGES = GPF_W_RING / WST_BYTES;
@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
             uint64_t* hs = (t & 1) ? &h_stored_odd[c] : &h_stored[c];
             ptx::mbar_arrive(hs);
             __threadfence();
-            ptx::mbar_arrive_remote_release(hs, crank ^ 1u);
+#pragma unroll
+            for (uint32_t pr = 1; pr < (uint32_t)CS; ++pr) ptx::mbar_arrive_remote_release(hs, (crank + pr) % (uint32_t)CS);
           } else {
             ptx::mbar_arrive(&h_stored[c]);
           }
@@ -535,9 +536,12 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   // column split (see the kernel's header comment): on unless IPN_GPF_CS=0; only where all the
   // CTAs of the doubled grid are co-resident (otherwise the second wave waits and nothing is gained)
   static const int cs_on = getenv("IPN_GPF_CS") ? atoi(getenv("IPN_GPF_CS")) : 1;
-  const bool cs = cs_on && (H / 64) % 2 == 0 && 2 * ntw * L->ndir <= 148;
-  const bool pair = !cs && pair_on && ntw % 2 == 0;
-  if (cs) p.timing = nullptr;
+  // 4 CTAs per row tile where that still fits one wave (a 4-CTA cluster grid places 132 CTAs): the 32-tile
+  // uni-directional layers of a 4096-measure batch -- the beat GRU and every tick of the argmax decode
+  const int cs = !cs_on ? 1 : ((H / 64) % 4 == 0 && cs_on != 2 && 4 * ntw * L->ndir <= 132) ? 4
+                             : ((H / 64) % 2 == 0 && 2 * ntw * L->ndir <= 148) ? 2 : 1;
+  const bool pair = cs == 1 && pair_on && ntw % 2 == 0;
+  if (cs > 1) p.timing = nullptr;
   char* wsp = reinterpret_cast<char*>(ws);
   bool save = false;
   for (int d = 0; d < L->ndir; ++d) {
@@ -603,13 +607,13 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
                    rows * H * 2.0 * (3 + 1 + (save ? GP_GATE_ARRAYS : 0) + (L->y ? 1 : 0)), stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(ntw * (cs ? 2 : 1), L->ndir, 1);
+    cfg.gridDim = dim3(ntw * cs, L->ndir, 1);
     cfg.blockDim = dim3(GP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (pair || cs) ? 2 : 1;
+    attr[0].val.clusterDim.x = pair ? 2 : cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -618,9 +622,11 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[6] = {false, false, false, false, false, false};
-  if (cs && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 2>, &cfgd[4]));
-  else if (cs) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 2>, &cfgd[5]));
+  static bool cfgd[8] = {false, false, false, false, false, false, false, false};
+  if (cs == 4 && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 4>, &cfgd[6]));
+  else if (cs == 4) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 4>, &cfgd[7]));
+  else if (cs == 2 && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 2>, &cfgd[4]));
+  else if (cs == 2) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 2>, &cfgd[5]));
   else if (save && pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, true, 1>, &cfgd[0]));
   else if (save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 1>, &cfgd[1]));
   else if (pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, true, 1>, &cfgd[2]));
