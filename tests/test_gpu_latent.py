@@ -228,3 +228,33 @@ def test_inference_batch_against_oracle_on_query_subsets(prec):
                 assert not bool(strict[r, i, k]), (int(rows[r]), i, k)
             k = min(k + 1, 24)
             assert rel_err(w[r, i, :k], w_ref[r, i, :k]) < tol, (int(rows[r]), i)
+
+
+def test_graphed_inpainter_replays_the_eager_call_bit_for_bit():
+    """inference.GraphedInpainter: LatentRNN.forward(..., train=False) captured in a CUDA graph gives, replay after
+    replay, exactly the tensors of the eager call on the same tokens and the same context-latent noise; with
+    fresh_noise=True the noise buffers change between replays (the reference draws rsample noise on every call)."""
+    from inpaintnet_b200.inference import GraphedInpainter
+    V, H, Z, Hc, Q = 20, 64, 32, 128, 256
+    n_p, n_t, n_f = 3, 2, 3
+    fx = dict(V=V, H=H, Z=Z, Hc=Hc, seed=1357)
+    m = build(fx, "bf16")
+    m.eval()
+    g = torch.Generator().manual_seed(3)
+    gi = GraphedInpainter(m, Q, n_p, n_t, n_f)
+    for rep in range(3):
+        score = torch.randint(0, V, (Q, n_p + n_t + n_f, 24), generator=g, dtype=torch.int32)
+        eps = [torch.randn(n_p * Q, Z, generator=g), torch.randn(n_f * Q, Z, generator=g)]
+        for dst, src in zip(gi.eps, eps):
+            dst.copy_(src)
+        w, s, z = gi(score.pin_memory(), fresh_noise=False)
+        torch.cuda.synchronize()
+        w, s, z = w.clone(), s.clone(), z.clone()
+        sd = score.to(DEV).long()
+        with torch.no_grad(), engine.inject_noise(eps=[e.clone() for e in eps]):
+            w2, s2, z2 = m(sd[:, :n_p], sd[:, n_p + n_t:], sd[:, n_p:n_p + n_t], n_t, train=False)
+        assert torch.equal(s, s2) and torch.equal(z, z2) and torch.equal(w, w2), rep
+    before = [e.clone() for e in gi.eps]
+    gi(score.pin_memory())
+    torch.cuda.synchronize()
+    assert all(not torch.equal(a, b) for a, b in zip(before, gi.eps))
