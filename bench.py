@@ -337,6 +337,31 @@ class Ctx:
         return kernels
 
 
+def standalone_wgrad(cx, B, reps=20):
+    """The dominant weight-gradient GEMM of the step -- dW_hh[1536, 512] += dP[24*B, 1536]^T . h[24*B, 512] of one
+    encoder-layer direction -- timed ALONE on an idle GPU (CUDA events, `reps` back-to-back launches, operands 403 MB:
+    larger than the L2).  Inside the step these GEMMs run on a side stream next to the persistent chain kernels, which
+    hold 128 of the 148 SMs, so their in-step launch durations (the `roofline` entry) mostly measure waiting for SMs;
+    this is the kernel's own rate."""
+    from inpaintnet_b200 import ops
+    rows, H3, Hh = 24 * B, 3 * H, H
+    dP = torch.randn(rows, H3, device="cuda").bfloat16()
+    hp = torch.randn(rows, Hh, device="cuda").bfloat16()
+    g = torch.zeros(H3, Hh, device="cuda")
+
+    def one(_i):
+        ops.gemm(ops.CORE_UMMA, ops.BF16, H3, Hh, [(dP.data_ptr(), H3, 1, hp.data_ptr(), Hh, 1, rows)], g.data_ptr(), ops.F32, Hh,
+                 accumulate=ops.ATOMIC_ADD)
+
+    for i in range(3):
+        one(i)
+    ms = cx.timed(one, reps) / reps
+    tf = 2.0 * rows * H3 * Hh / (ms * 1e-3) / 1e12
+    return {"kernel": "gemm_umma_tn_wgrad", "shape": f"dW[{H3},{Hh}] += dP[{rows},{H3}]^T h[{rows},{Hh}]", "launch_us": ms * 1e3,
+            "achieved": tf, "unit": "TFLOP/s", "peak": cx.tf_peak, "frac": tf / cx.tf_peak,
+            "how": f"{reps} launches alone on an idle GPU, CUDA events; algorithmic bytes {(rows * (H3 + Hh) * 2) / 1e6:.0f} MB per launch"}
+
+
 # ---------------------------------------------------------------------------------------------
 # section: MeasureVAE training step (configs[1]) -- the headline metric
 # ---------------------------------------------------------------------------------------------
@@ -405,7 +430,8 @@ def run_mvae(cx, K, W):
     trainer.check_device_flags()
     kernels = cx.profile(step_resident, max(2, args.profile_steps) // 2 * 2)   # equal numbers of TF and argmax steps
     dec.teacher_forcing_prob = 0.5
-    out = dict(B=B, K=K, ms=ms, ms_e2e=ms_e2e, launches=launches, modes=modes, kernels=kernels)
+    standalone = standalone_wgrad(cx, B)
+    out = dict(B=B, K=K, ms=ms, ms_e2e=ms_e2e, launches=launches, modes=modes, kernels=kernels, standalone=standalone)
     del trainer, model
     torch.cuda.empty_cache()
     return out
@@ -674,6 +700,10 @@ def main():
         e2e_value = world * B * K / (ms_e2e / 1e3)
         kernels = mv["kernels"]
         roofline, crit = cx.rooflines(kernels, critical=("gru_layer_fwd_persist", "gru_layer_bwd_persist"))
+        if roofline is not None:
+            roofline["standalone"] = mv["standalone"]
+            roofline["note"] = ("achieved = in-step launch durations (side stream, next to chain kernels that hold 128 SMs); "
+                                "standalone = the same kernel alone on the GPU")
         # the serial chain: per-step latency of one encoder-layer step against the floors of DESIGN.md section 4.3
         # (12.9 GFLOP at the sustained tensor peak; 84 MB of algorithmic bytes at the measured HBM rate)
         for c in crit:

@@ -211,6 +211,10 @@ class ParamArena:
         if mark is not None:
             cur = torch.cuda.current_stream()
             if cur != mark[0]:
+                if torch.cuda.is_current_stream_capturing():
+                    # a capturing stream cannot wait on an event recorded outside the capture; the caches were filled
+                    # by eager work that the caller synchronised with before starting the capture (GraphedInpainter)
+                    return
                 cur.wait_event(mark[1])
 
     def w(self, prec, name, col0=0, cols=None):

@@ -42,6 +42,8 @@ class GraphedInpainter:
                     torch.empty(n_future * queries, Z, dtype=torch.float32, device=dev)]  # static noise
         self._arena = arena
         self.refresh_noise()
+        # warm-up and capture run on ONE side stream: the arena's caches (bf16 weight pack, derived tables) remember the
+        # stream that filled them and make other streams wait on an event -- which a capturing stream must not do
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):          # eager warm-up: derived tables, weight pack, TMA descriptors, kernel attributes
@@ -50,7 +52,7 @@ class GraphedInpainter:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.out = self._body()
         arena.range_flag.zero_()
 
