@@ -133,9 +133,10 @@ def _run_reference_script(script, **kwargs):
     click main() body under the stub library (plumbing only: argument wiring, shapes, state_dict / checkpoint files)."""
     import importlib.util
     import sys
-    ref = "/root/reference/" + script
+    from oracle.ref_import import REFERENCE_ROOT
+    ref = os.path.join(REFERENCE_ROOT, script)
     if not os.path.exists(ref) or torch.cuda.is_available():
-        pytest.skip("reference tree not mounted (or GPU box)")
+        pytest.skip("reference neither mounted nor staged, or a GPU box (tests/test_gpu_scripts.py runs the real library there)")
     dropin = os.path.join(ROOT, "inpaintnet_b200", "dropin")
     tops = ("MeasureVAE", "LatentRNN", "utils", "DatasetManager", "AnticipationRNN")
     saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k.split(".")[0] in tops}
