@@ -42,7 +42,7 @@ def _run(script, **kwargs):
         orig = D.SyntheticFolkDataset.__init__
 
         def small(self, *a, **k):
-            k["num_sequences"] = 16
+            k["num_sequences"] = 40   # 28 train / 8 validation / 4 test sequences: at least one batch of 4 in every split
             k.setdefault("num_notes", 20)
             orig(self, *a, **k)
 
