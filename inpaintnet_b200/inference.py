@@ -52,7 +52,8 @@ class GraphedInpainter:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
+        # thread_local: other threads of the process (NCCL watchdog under torchrun, data loaders) may call CUDA meanwhile
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
             self.out = self._body()
         arena.range_flag.zero_()
 
