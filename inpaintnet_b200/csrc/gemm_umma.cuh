@@ -558,47 +558,29 @@ umma_gemm_persist_kernel(const __grid_constant__ UmmaBatch<Epi> batch, int ntx, 
       ptx::mbar_wait(&tmem_full[b], n & 1);
       ptx::tc_fence_after();
       if (tile_ok) {
-        // 16 accumulator columns (output rows) per pass; the TMEM load of the NEXT pass is in flight while this one is
-        // applied and stored (short-K GEMMs -- input projections, K <= 1024 -- are bound by this loop, not by the MMAs)
-        auto valid = [&](int c) { return c < BR / 16 && ti.r0 + c * 16 < P.M; };   // warp uniform
-        auto load = [&](int c, float (&dst)[16]) {
-          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BR + c * 16), dst);
-        };
-        auto apply = [&](int c, float (&acc)[16]) {
+#pragma unroll 1
+        for (int c = part; c < BR / 16; c += Cfg::PARTS) {
           const int row0 = ti.r0 + c * 16;
+          if (row0 >= P.M) break;  // warp uniform
+          float acc[1][16];
+          if (nchunks > 0) {
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BR + c * 16), acc[0]);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[0][i] = 0.f;
+          }
           const int nv = min(16, P.M - row0);
           if (col_ok) {
             float a8[1][8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a8[0][i] = acc[h * 8 + i];
+              for (int i = 0; i < 8; ++i) a8[0][i] = acc[0][h * 8 + i];
               const int nvh = nv - h * 8;
               if (nvh > 0) Epi::template applyT<8>(P.epi, cc, col, row0 + h * 8, min(8, nvh), a8);
             }
           }
-        };
-        float accA[16], accB[16];
-        int c = part;
-        if (nchunks > 0) {
-          if (valid(c)) load(c, accA);
-#pragma unroll 1
-          while (valid(c)) {
-            const int c1 = c + Cfg::PARTS, c2 = c1 + Cfg::PARTS;
-            ptx::tmem_ld_wait16(accA);
-            if (valid(c1)) load(c1, accB);
-            apply(c, accA);
-            if (!valid(c1)) break;
-            ptx::tmem_ld_wait16(accB);
-            if (valid(c2)) load(c2, accA);
-            apply(c1, accB);
-            c = c2;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) accA[i] = 0.f;
-#pragma unroll 1
-          for (; valid(c); c += Cfg::PARTS) apply(c, accA);
         }
       }
       ptx::tc_fence_before();
