@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
       ptx::mbar_init(dg_ready, 16);
       ptx::mbar_init(dp_read, 1);
       ptx::mbar_init(mma_all, NC);
-      ptx::mbar_init(recv_full, (NC - 1) * 16);
+      ptx::mbar_init(recv_full, 1);   // one local arrive.expect_tx per GEMM phase + the bytes of the peers' st.async
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -414,7 +414,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
         __syncwarp();
         // the peers write their partial sums into this CTA's A tile once mma_all fires: the dP stores must have read it
         ptx::mbar_wait(dp_read, it & 1);
-        if (ptx::elect_one()) ptx::umma_commit_multicast(mma_all, (uint16_t)((1u << NC) - 1u));
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(recv_full, (NC - 1) * LP_KB);   // armed before any peer can send (they wait for mma_all)
+          ptx::umma_commit_multicast(mma_all, (uint16_t)((1u << NC) - 1u));
+        }
         __syncwarp();
       }
     } else if (warp == 2) {
@@ -555,15 +558,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lstm_persist_bwd_kernel(const _
           ptx::tmem_ld16(tlane + (uint32_t)(peer * 64 + sub * 16), part);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int v = 0; v < 2; ++v)
-            st_cluster_u4(send_base[pr] + (uint32_t)row * 128u + ((((uint32_t)(sub * 2 + v)) ^ sw) << 4), pack8(part + 8 * v));
+          for (int v = 0; v < 2; ++v) {
+            const uint4 u = pack8(part + 8 * v);
+            ptx::st_async_v4(send_base[pr] + (uint32_t)row * 128u + ((((uint32_t)(sub * 2 + v)) ^ sw) << 4), u.x, u.y, u.z, u.w, send_bar[pr]);
+          }
         }
         ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int pr = 1; pr < NC; ++pr) ptx::mbar_arrive_cluster(send_bar[pr]);
-        }
         if (tm) { w_mma += c3 - c2; w_s += clock64() - c3; }
       }
     }

@@ -301,6 +301,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// asynchronous 16-byte store into the shared memory of another CTA of the cluster; the bytes are accounted (complete_tx) on
+// the DESTINATION CTA's mbarrier, so the sender needs no release fence / arrive (and never waits for an acknowledgement)
+__device__ __forceinline__ void st_async_v4(uint32_t dst_caddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t bar_caddr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(dst_caddr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar_caddr)
+               : "memory");
+}
 // bulk copy from this CTA's shared memory into the shared memory of another CTA of the cluster (dst / bar: shared::cluster
 // addresses from mapa); the bytes are accounted (complete_tx) on the DESTINATION CTA's mbarrier
 __device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_caddr, uint32_t src_saddr, uint32_t bytes, uint32_t bar_caddr) {
