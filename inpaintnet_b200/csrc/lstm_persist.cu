@@ -13,7 +13,11 @@
 //   * backward, per step: the CTA differentiates its own 64 units (dG = [di, df, dg, do], written to the A tile and
 //     TMA-stored to dP for the hoisted weight-gradient GEMMs), multiplies dG[128, 4 x 64] by its W_hh rows (K-split of
 //     dh_{t-1} = dG . W_hh: a partial sum over its 256 gate rows for ALL H columns) and reduce-scatters the partial
-//     sums to the owners of the columns through distributed shared memory (bf16 partials, fp32 sum).
+//     sums to the owners of the columns through distributed shared memory (st.async with the bytes accounted on the
+//     receiver's mbarrier; bf16 partials, fp32 sum).
+// Forward exchange: the 16 KB h_t slice goes to every peer as ONE bulk DSMEM copy (cp.async.bulk shared::cta ->
+// shared::cluster, complete_tx on the peer's barrier) issued by the store warp once the 16 epilogue warps have written
+// the local copy; measured (tests/dev/lstm_persist_time.py) remote st.shared::cluster from all threads ran at ~7 B/clk/SM.
 // Per-element tensors that only these kernels touch use the blocked layout of gru_persist.cuh (coalesced 16-byte
 // vectors): the input projection P (4 arrays, produced directly by ipn_lstm_inproj_blocked) and the saved state
 // (5 arrays: i, f, g, o, c_t).  h (row-major, read by the hoisted GEMMs) leaves through TMA stores from the A tile.
