@@ -206,7 +206,10 @@ typedef struct {
   void* final_out_dir; /* when non-null: this direction writes its final state here instead of IpnGruLayer.final_out */
   int final_dir_dt;
   long long ld_final_dir;
-  int P_blocked; /* P was produced by ipn_gru_inproj_blocked (persistent kernel only; table/pvec must be null) */
+  int P_blocked; /* P was produced by ipn_gru_inproj_blocked (persistent kernel only; pvec must be null; a table is
+                    allowed only in the two-term form P_bcast = 1, table_rows in (0, 128]: P is then ONE blocked
+                    [B_total, 3, H] tile set reused at every step -- the per-beat part of the tick GRU's layer-0
+                    projection, b_ih and b_hh folded in -- and the table row of tok is added in the epilogue) */
   int table_rows; /* rows of `table` (0 = unknown).  Known and <= 128 with no other input-projection term: the
                      persistent kernel's blocked P is gathered from a folded bf16 copy of the table (HBM write bound) */
 } IpnGruDir;

@@ -385,6 +385,41 @@ __global__ void fill_i32_kernel(int* dst, long long n, int value) {
   if (i < n) dst[i] = value;
 }
 
+// bf16 fast path: one 16-byte vector (8 columns) per thread and slot, fp32 sums, 16-byte store
+__global__ void sum_slots_vec_kernel(const __nv_bfloat16* X, long long ld, int slots, long long rows, int cols,
+                                     __nv_bfloat16* out, long long ld_out) {
+  const int vpr = cols >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * vpr) return;
+  const long long r = i / vpr;
+  const int c = (int)(i - r * vpr) << 3;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int s0 = 0; s0 < slots; s0 += 6) {
+    uint4 u[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (s0 + j < slots) u[j] = *reinterpret_cast<const uint4*>(X + ((long long)(s0 + j) * rows + r) * ld + c);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (s0 + j < slots) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h2[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+  }
+  uint4 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+  *reinterpret_cast<uint4*>(out + r * ld_out + c) = o;
+}
+
 __global__ void sum_slots_kernel(const void* X, int dt, long long ld, int slots, long long rows, int cols, void* out,
                                  long long ld_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -605,7 +640,13 @@ int ipn_sum_slots(const void* X, int dt, long long ld, int slots, long long rows
   IPN_PROPAGATE(ensure_device());
   ProfScope prof("sum_slots", 0.0, (double)((double)(slots + 1) * rows * cols * (dt == IPN_BF16 ? 2.0 : 4.0)), STREAM);
   IPN_REQUIRE(X && out && slots > 0 && rows > 0 && cols > 0, IPN_ERR_ARG, "sum_slots: bad args");
-  sum_slots_kernel<<<cdiv(rows * cols, 256), 256, 0, STREAM>>>(X, dt, ld, slots, rows, cols, out, ld_out);
+  if (dt == IPN_BF16 && cols % 8 == 0 && ld % 8 == 0 && ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(X) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    sum_slots_vec_kernel<<<cdiv(rows * (cols / 8), 256), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(X), ld, slots, rows,
+                                                                         cols, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  } else {
+    sum_slots_kernel<<<cdiv(rows * cols, 256), 256, 0, STREAM>>>(X, dt, ld, slots, rows, cols, out, ld_out);
+  }
   IPN_LAUNCH_CHECK();
   return IPN_OK;
 }

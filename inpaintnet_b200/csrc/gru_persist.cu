@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(256) gru_prep_p_kernel(PrepP p) {
 // r,z and bf16(table) for n) and the layer kernel's epilogue gathers its rows by token id (L2-resident, 3H * 2 B per
 // row) -- for 98304 context measures that removes 14.5 GB of HBM writes and the same amount of reads per layer.
 __global__ void gru_fold_table_kernel(const float* table, long long ld_table, int rows, const float* b_hh, int H,
-                                      __nv_bfloat16* out) {
+                                      __nv_bfloat16* out) {   // b_hh == nullptr: it is folded into the other P term
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 3 * H) return;
   const int r = i / (3 * H), c = i - r * 3 * H;
   float f = 0.f;
   f += table[(long long)r * ld_table + c];
-  const float cst = c < 2 * H ? b_hh[c] : 0.f;
+  const float cst = (c < 2 * H && b_hh != nullptr) ? b_hh[c] : 0.f;
   out[i] = __float2bfloat16_rn((f + cst) * (c < 2 * H ? 0.5f : 1.f));
 }
 
@@ -378,6 +378,23 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
         for (int g = 0; g < 3; ++g)
 #pragma unroll
           for (int v = 0; v < 2; ++v) dst[g][v] = ldp ? __ldg(base + g * vpr + v) : make_uint4(0, 0, 0, 0);
+        if (D.Pblk != nullptr) {
+          // two-term projection (tick GRU layer 0): table row of the previous token + the per-beat projection, the
+          // latter a blocked tile that is the same for every step of the call (p_t_stride == 0)
+          const long long rtb = (long long)tt * D.p_t_stride + D.p_t0 + tile_x;
+          const uint4* pb = D.Pblk + (rtb * 3 * vpr + c * 8 + sub * 2) * 128 + row;
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              float a[8], b[8];
+              unpack8(dst[g][v], a);
+              unpack8(ldg_stream(pb + (g * vpr + v) * 128), b);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) a[k] += b[k];
+              dst[g][v] = pack8(a);
+            }
+        }
         return;
       }
       const long long rt = (long long)tt * D.p_t_stride + D.p_t0 + tile_x;
@@ -482,6 +499,7 @@ bool persist_enabled() {
 }
 
 static bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+static bool dir_gathers_table_plus_bcast(const IpnGruDir& D);
 
 bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
   if (!persist_enabled()) return false;
@@ -497,13 +515,20 @@ bool gru_persist_fwd_shape_ok(const IpnGruLayer* L) {
     if (D.y_col0 % 8 != 0) return false;
     if (D.P != nullptr && (D.ldP % 8 != 0 || !al16(D.P))) return false;
     if (D.table != nullptr && (D.ld_table % 4 != 0 || !al16(D.table))) return false;
-    if (D.P_blocked && (D.P == nullptr || D.table != nullptr || D.pvec != nullptr || D.P_bcast)) return false;
+    if (D.P_blocked && (D.P == nullptr || D.pvec != nullptr)) return false;
+    // blocked P + token table: only as the two-term form (broadcast blocked tile + gathered table row)
+    if (D.P_blocked && (D.table != nullptr || D.P_bcast) && !dir_gathers_table_plus_bcast(D)) return false;
     if (D.gates != nullptr && !al16(D.gates)) return false;
   }
   return true;
 }
 
 constexpr int GPF_FOLD_ROWS = 128;   // largest token table the gather path folds (vocabularies are 45-90 symbols)
+// two-term input projection: P (blocked, one [B_total, 3, H] tile set reused at every step, biases folded in) + table[tok]
+static bool dir_gathers_table_plus_bcast(const IpnGruDir& D) {
+  return D.table != nullptr && D.tok != nullptr && D.P != nullptr && D.P_blocked && D.P_bcast && D.pvec == nullptr &&
+         D.table_rows > 0 && D.table_rows <= GPF_FOLD_ROWS;
+}
 static bool dir_gathers_table(const IpnGruDir& D) {
   static const int on = getenv("IPN_GPF_GATHER") ? atoi(getenv("IPN_GPF_GATHER")) : 1;
   return on && D.table != nullptr && D.tok != nullptr && D.P == nullptr && D.pvec == nullptr && !D.P_blocked &&
@@ -515,7 +540,8 @@ long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L) {
   const long long per_dir = (long long)(L->s_end - L->s_begin) * L->nrows * 3 * L->H * 2;
   long long total = 0;   // per direction: the folded token table, or the blocked P of this call's window, or nothing
   for (int d = 0; d < L->ndir; ++d)
-    total += dir_gathers_table(L->dir[d]) ? GPF_FOLD_ROWS * 3LL * L->H * 2 : (L->dir[d].P_blocked ? 0 : per_dir);
+    total += (dir_gathers_table(L->dir[d]) || dir_gathers_table_plus_bcast(L->dir[d])) ? GPF_FOLD_ROWS * 3LL * L->H * 2
+                                                                                          : (L->dir[d].P_blocked ? 0 : per_dir);
   return total > 16 ? total : 16;
 }
 
@@ -560,15 +586,21 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     o.gates = reinterpret_cast<uint4*>(D.gates);
     save = save || D.gates != nullptr;
     const int tt_min = D.reverse ? T - L->s_end : L->s_begin;   // earliest time index this call touches
-    if (dir_gathers_table(D)) {
+    if (dir_gathers_table(D) || dir_gathers_table_plus_bcast(D)) {
+      const bool plus = dir_gathers_table_plus_bcast(D);
       __nv_bfloat16* ft = reinterpret_cast<__nv_bfloat16*>(wsp);
       ProfScope prof("gru_fold_table", 0.0, (double)D.table_rows * 3 * H * 6, stream);
       gru_fold_table_kernel<<<(D.table_rows * 3 * H + 255) / 256, 256, 0, stream>>>(D.table, D.ld_table, D.table_rows,
-                                                                                    D.b_hh, H, ft);
+                                                                                    plus ? nullptr : D.b_hh, H, ft);
       IPN_LAUNCH_CHECK();
       o.ftab = reinterpret_cast<const uint4*>(ft);
       o.tok = D.tok;
       o.Pblk = nullptr;
+      if (plus) {   // the blocked per-row term: same tiles at every step
+        o.Pblk = reinterpret_cast<const uint4*>(D.P);
+        o.p_t_stride = 0;
+        o.p_t0 = L->row0 / GP_ROWS;
+      }
       wsp += GPF_FOLD_ROWS * 3LL * H * 2;
     } else if (D.P_blocked) {
       o.Pblk = reinterpret_cast<const uint4*>(D.P);   // global blocked layout over all T*Bt rows

@@ -123,7 +123,7 @@ def bigru2_backward(arena, pfx, prec, saved, dY1=None, dh_n=None, dh0=None):
                 ops.gemm(CORE_SIMT, F32, 3 * H, 1, [(sv.data_ptr(), 1, 0, arena.fptr(x[1]), 1, 0, 1)], arena.gptr(n_ih), F32, 1,
                          accumulate=ATOMIC_ADD, split_k=1)
                 ops.gemm(CORE_SIMT, F32, 1, 1, [(sv.data_ptr(), 3 * H, 0, arena.fptr(n_ih), 3 * H, 0, 3 * H)], arena.gptr(x[1]),
-                         F32, 1, accumulate=ATOMIC_ADD, split_k=1)
+                         F32, 1, accumulate=ATOMIC_ADD, split_k=32)
 
 
 def _encode_z(arena, prec, model, tokens, n_noise_rows):
