@@ -1,8 +1,10 @@
 // Persistent GRU layer kernels (forward and backward): one launch runs ALL timesteps of a layer.
 //
-// A CTA owns a tile of 128 batch rows of one direction for the whole sequence, so the serial chain
-// needs no grid-wide synchronisation: the only cross-step hand-off is inside the CTA (TMA store of
-// h_t -> TMA reload as the next step's A operand, tracked per 64-unit k-block with mbarriers).
+// A CTA (or, with the column split, a cluster of 2 / 4 CTAs that share the tile and own 1/2 / 1/4 of the
+// hidden units each) owns a tile of 128 batch rows of one direction for the whole sequence, so the serial
+// chain needs no grid-wide synchronisation: the only cross-step hand-off is inside the CTA / cluster (TMA
+// store of h_t -> TMA reload as the next step's A operand, tracked per 64-unit k-block with mbarriers;
+// across the CTAs of a cluster the barriers are signalled remotely with release/acquire at cluster scope).
 // "Lanes = batch rows": MMA M = 128 rows (TMEM lanes), N = 3 gates x 64 hidden units per chunk
 // (forward) so one thread holds r, z, n of 16 consecutive units of ITS row per tcgen05.ld.  All
 // per-element traffic of the epilogue uses the BLOCKED layout below (16-byte vectors, fully
