@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "lib", "libinpaintnet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-SOURCES = ["runtime.cu", "gemm_api.cu", "gru_api.cu", "gru_persist.cu", "gru_persist_bwd.cu", "lstm_api.cu", "lstm_persist.cu", "decoder_api.cu", "elementwise.cu"]
+SOURCES = ["runtime.cu", "gemm_api.cu", "gru_api.cu", "gru_persist.cu", "gru_persist_bwd.cu", "lstm_api.cu", "lstm_persist.cu", "tick_persist.cu", "decoder_api.cu", "elementwise.cu"]
 
 
 def _deps():

@@ -6,6 +6,9 @@ using namespace ipn;
 namespace ipn {
 bool gru_persist_fwd_shape_ok(const IpnGruLayer* L);
 long long gru_persist_fwd_ws_bytes(const IpnGruLayer* L);
+// tick_persist.cu: the whole decode as one persistent kernel
+bool tick_persist_shape_ok(const IpnTickDecode* p);
+int tick_persist_decode(const IpnTickDecode* p, void* ws, long long ws_bytes, cudaStream_t stream);
 }
 
 // the two per-tick GRU layer descriptors (row window = beat i of the batch, one step)
@@ -34,7 +37,8 @@ static bool tick_persist_ok(const IpnTickDecode* p) {
 }
 
 extern "C" long long ipn_tick_decode_ws_bytes(const IpnTickDecode* p) {
-  if (p == nullptr || !tick_persist_ok(p)) return 0;
+  if (p == nullptr) return 0;
+  if (!tick_persist_ok(p)) return tick_persist_shape_ok(p) ? 128LL * 3 * p->H * 2 : 0;
   IpnGruLayer L0, L1;   // both per-tick layer calls share the workspace (stream ordered): the larger requirement
   tick_layers(p, L0, L1);
   L1.dir[0].P_blocked = 1;
@@ -51,6 +55,10 @@ extern "C" int ipn_tick_decode_argmax(const IpnTickDecode* p, void* stream) {
   const int B = p->B, H = p->H, V = p->V, dt = p->act_dt;
   const long long B4 = 4LL * B;
   const long long es = dt == IPN_BF16 ? 2 : 4;
+
+  // one launch for all 24 ticks where the 4-CTA-per-tile grid is co-resident (batches up to 4224 measures)
+  if (p->ws != nullptr && tick_persist_shape_ok(p) && p->ws_bytes >= 128LL * 3 * H * 2)
+    return tick_persist_decode(p, p->ws, p->ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 
   IpnGruLayer L0, L1;
   tick_layers(p, L0, L1);

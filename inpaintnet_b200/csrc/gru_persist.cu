@@ -87,6 +87,14 @@ __global__ void gru_fold_table_kernel(const float* table, long long ld_table, in
   out[i] = __float2bfloat16_rn((f + cst) * (c < 2 * H ? 0.5f : 1.f));
 }
 
+int gru_fold_table(const float* table, long long ld_table, int rows, const float* b_hh, int H, void* out, cudaStream_t stream) {
+  ProfScope prof("gru_fold_table", 0.0, (double)rows * 3 * H * 6, stream);
+  gru_fold_table_kernel<<<(rows * 3 * H + 255) / 256, 256, 0, stream>>>(table, ld_table, rows, b_hh, H,
+                                                                         reinterpret_cast<__nv_bfloat16*>(out));
+  IPN_LAUNCH_CHECK();
+  return IPN_OK;
+}
+
 // y[R, col0 + u] = keep[R, col0 + u] ? y * scale : 0   (inter-layer dropout applied after the layer kernel)
 __global__ void gru_mask_y_kernel(__nv_bfloat16* y, long long ld_y, const unsigned char* mask, long long ld_mask,
                                   int col0, int H, long long rows, float scale, int nrows, int Bt, int tt_min, int row0) {
@@ -305,9 +313,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           if (CS > 1) {   // the peer reloads this chunk of h_t from L2 as a k-block of its next step's A operand
             uint64_t* hs = (t & 1) ? &h_stored_odd[c] : &h_stored[c];
             ptx::mbar_arrive(hs);
-            __threadfence();
+            ptx::fence_acq_rel_cluster();   // one release fence, then relaxed remote arrives (see ptx.cuh)
 #pragma unroll
-            for (uint32_t pr = 1; pr < (uint32_t)CS; ++pr) ptx::mbar_arrive_remote_release(hs, (crank + pr) % (uint32_t)CS);
+            for (uint32_t pr = 1; pr < (uint32_t)CS; ++pr) ptx::mbar_arrive_remote_relaxed(hs, (crank + pr) % (uint32_t)CS);
           } else {
             ptx::mbar_arrive(&h_stored[c]);
           }

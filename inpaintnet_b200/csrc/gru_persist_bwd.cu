@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           if (CS > 1) {   // the peer streams these dP / dGn chunks as k-blocks of its GEMM phase
             uint64_t* ds = (it & 1) ? &dg_stored_odd[c] : &dg_stored[c];
             ptx::mbar_arrive(ds);
-            __threadfence();
-            ptx::mbar_arrive_remote_release(ds, crank ^ 1u);
+            ptx::fence_acq_rel_cluster();
+            ptx::mbar_arrive_remote_relaxed(ds, crank ^ 1u);
           } else {
             ptx::mbar_arrive(&dg_stored[c]);
           }

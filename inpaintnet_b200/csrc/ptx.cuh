@@ -215,6 +215,19 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32
       "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// One fence + relaxed remote arrives is the cheap form of the same hand-off (measured in the tick-decode kernel: a
+// release.cluster arrive costs 1.0-1.9 kcycles EACH -- it waits for the previous remote arrive's acknowledgement --
+// and __threadfence() another 1.3 kcycles; fence.acq_rel.cluster once, then fire-and-forget arrives).
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
 // TMA load issued by either CTA of a pair; the bytes are accounted on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0, int crd1) {
   asm volatile(
