@@ -137,7 +137,7 @@ static inline int gpf_smem_bytes(int H) {
 // h_stored[chunk] barrier once the store has completed; the A loaders reload all k-blocks from L2 as before.
 template <bool SAVE, bool PAIR, int CS>
 __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __grid_constant__ GruPersistFwd p) {
-  static_assert(CS == 1 || ((CS == 2 || CS == 4) && !PAIR), "column split uses plain (cta_group::1) MMAs");
+  static_assert(CS == 1 || CS == 2 || (CS == 4 && !PAIR), "column split: 2 or 4 CTAs per tile, or 2 CTA pairs per two tiles");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int WST_BYTES = PAIR ? GPF_W_BYTES / 2 : GPF_W_BYTES;  // per-CTA bytes of one W stage
   constexpr int WSTAGES = GPF_W_RING / WST_BYTES;
@@ -146,13 +146,17 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   const int H = p.H, KB = H >> 6, T = p.T;
   const int NS = p.s_end - p.s_begin;   // processing steps s_begin .. s_end-1 (loop index t = s - s_begin)
   const int Bt = p.Bt;
-  const int tile_x = CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x;   // row tile of this CTA
-  const int rbase = p.row0 + tile_x * GP_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = (PAIR || CS > 1) ? ptx::cluster_ctarank() : 0u;
-  const uint32_t rank = PAIR ? crank : 0u;          // pair: which half of the M = 256 tile / of every W stage
-  const bool leader = rank == 0;                    // column split: both CTAs run their own complete pipeline
-  const int c_lo = CS > 1 ? (int)crank * (KB / CS) : 0, c_hi = c_lo + KB / CS;   // chunks (64 hidden units) of this CTA
+  const uint32_t rank = PAIR ? (crank & 1u) : 0u;   // pair: which half of the M = 256 tile / of every W stage
+  const bool leader = rank == 0;                    // column split: every CTA (pair) runs its own complete pipeline
+  const uint32_t lead_rank = crank & ~1u;           // cluster rank of this pair's leader CTA
+  // PAIR + CS = 2: a cluster of 4 = two pairs; pair `crank >> 1` owns half of the hidden units of TWO adjacent row tiles
+  const uint32_t colrank = PAIR ? (crank >> 1) : crank;
+  const int tile_x = PAIR ? ((int)blockIdx.x / (2 * CS)) * 2 + (int)rank : (int)blockIdx.x / CS;   // row tile of this CTA
+  const int rbase = p.row0 + tile_x * GP_ROWS;
+  const uint16_t pair_mask = (uint16_t)(3u << lead_rank);
+  const int c_lo = CS > 1 ? (int)colrank * (KB / CS) : 0, c_hi = c_lo + KB / CS;   // chunks (64 hidden units) of this CTA
 
   uint8_t* sA = smem;
   uint8_t* sW = sA + KB * GP_KB_BYTES;
@@ -271,8 +275,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
                 else ptx::umma_bf16(dcol, da0 + (uint64_t)(kk * 2), dw0 + (uint64_t)(kk * 2), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
               }
               if (PAIR) {
-                ptx::umma_commit_pair(&w_empty[stage]);
-                if (c == c_hi - 1) ptx::umma_commit_pair(&a_free[kb]);
+                ptx::umma_commit_pair(&w_empty[stage], pair_mask);
+                if (c == c_hi - 1) ptx::umma_commit_pair(&a_free[kb], pair_mask);
               } else {
                 ptx::umma_commit(&w_empty[stage]);
                 if (c == c_hi - 1) ptx::umma_commit(&a_free[kb]);
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
             if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
           }
           if (ptx::elect_one()) {
-            if (PAIR) ptx::umma_commit_pair(&tmem_full[b]);
+            if (PAIR) ptx::umma_commit_pair(&tmem_full[b], pair_mask);
             else ptx::umma_commit(&tmem_full[b]);
           }
           __syncwarp();
@@ -314,8 +318,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
             uint64_t* hs = (t & 1) ? &h_stored_odd[c] : &h_stored[c];
             ptx::mbar_arrive(hs);
             ptx::fence_acq_rel_cluster();   // one release fence, then relaxed remote arrives (see ptx.cuh)
+            if (PAIR) {
+              ptx::mbar_arrive_remote_relaxed(hs, crank ^ 2u);   // same rows, the other half of the hidden units
+            } else {
 #pragma unroll
-            for (uint32_t pr = 1; pr < (uint32_t)CS; ++pr) ptx::mbar_arrive_remote_relaxed(hs, (crank + pr) % (uint32_t)CS);
+              for (uint32_t pr = 1; pr < (uint32_t)CS; ++pr) ptx::mbar_arrive_remote_relaxed(hs, (crank + pr) % (uint32_t)CS);
+            }
           } else {
             ptx::mbar_arrive(&h_stored[c]);
           }
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       __syncwarp();
       if (lane == 0) {
         if (leader) ptx::mbar_arrive(&tmem_empty[b]);
-        else ptx::mbar_arrive_remote(&tmem_empty[b], 0);
+        else ptx::mbar_arrive_remote(&tmem_empty[b], lead_rank);
         ptx::mbar_arrive(stg_ready);
       }
     };
@@ -574,7 +582,11 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   // uni-directional layers of a 4096-measure batch -- the beat GRU and every tick of the argmax decode
   const int cs = !cs_on ? 1 : ((H / 64) % 4 == 0 && cs_on != 2 && 4 * ntw * L->ndir <= 132) ? 4
                              : ((H / 64) % 2 == 0 && 2 * ntw * L->ndir <= 148) ? 2 : 1;
-  const bool pair = cs == 1 && pair_on && ntw % 2 == 0;
+  // two CTA pairs per two row tiles (M = 256 MMAs on half of the hidden units each): every CTA stages HALF of each W_hh
+  // tile, so the same ring holds twice as many tiles in flight -- the streaming rate of these kernels is (bytes in
+  // flight) / (commit -> refill -> landed round trip), not L2 bandwidth.  IPN_GPF_PAIRCS=0 keeps the plain column split.
+  static const int paircs_on = getenv("IPN_GPF_PAIRCS") ? atoi(getenv("IPN_GPF_PAIRCS")) : 1;
+  const bool pair = pair_on && ntw % 2 == 0 && (cs == 1 || (cs == 2 && paircs_on && 2 * ntw * L->ndir <= 132));
   if (cs > 1) p.timing = nullptr;
   char* wsp = reinterpret_cast<char*>(ws);
   bool save = false;
@@ -653,7 +665,7 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : cs;
+    attr[0].val.clusterDim.x = pair ? 2 * cs : cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -662,8 +674,10 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[8] = {false, false, false, false, false, false, false, false};
-  if (cs == 4 && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 4>, &cfgd[6]));
+  static bool cfgd[10] = {false, false, false, false, false, false, false, false, false, false};
+  if (cs == 2 && pair && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, true, 2>, &cfgd[8]));
+  else if (cs == 2 && pair) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, true, 2>, &cfgd[9]));
+  else if (cs == 4 && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 4>, &cfgd[6]));
   else if (cs == 4) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 4>, &cfgd[7]));
   else if (cs == 2 && save) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<true, false, 2>, &cfgd[4]));
   else if (cs == 2) IPN_PROPAGATE(launch(gru_persist_fwd_kernel<false, false, 2>, &cfgd[5]));

@@ -267,9 +267,10 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a,
       : "memory");
 }
 // arrives on the mbarrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+// (cta_mask: the two CTAs of the pair within the cluster -- 3 for a 2-CTA cluster, 3 << 2k for pair k of a larger one)
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((unsigned short)3)
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 

@@ -244,9 +244,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
       int n_load = 0;              // refills of the A tile so far
       int n_write[2] = {0, 0};     // fresh accumulations started in TMEM buffer b
       unsigned prev_key = 0xffffffffu;
-      const bool tm = p.timing != nullptr;
-      long long w_te = 0, w_af = 0, w_wf = 0, w_lg = 0;
+      const bool tm = p.timing != nullptr && (p.dbg & 16);   // wait counters cost ~150 cycles per clock64: off unless asked
+      long long w_te = 0, w_af = 0, w_wf = 0, w_lg = 0, w_is = 0, w_cm = 0, w_kb = 0;
       const long long t_begin = clock64();
+      unsigned long long gt0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
       const uint64_t descA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024);
       const uint64_t descW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024);
       int kind, t;
@@ -270,13 +272,15 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           if (lane == 0 && ci == 0) tr(0, kind == PH_BX || kind == PH_V ? t : t - 1, kind * 4);   // TMEM free: phase starts
           const uint32_t dbase = tmem_base + (uint32_t)(b * 256);
           for (int kb = 0; kb < KB; ++kb) {
+            const long long tk0 = tm ? clock64() : 0;
             if (reload && ci == 0) wait_acc(&a_full[kb], (uint32_t)(n_load & 1), tm, w_af);
             wait_acc(&w_full[stage], phase, tm, w_wf);
-            ptx::tc_fence_after();
+            if (!(p.dbg & 4)) ptx::tc_fence_after();
             if (lane == 0 && ci == 0 && kb == 0) tr(0, kind == PH_BX || kind == PH_V ? t : t - 1, kind * 4 + 1);   // first operands landed
             const uint64_t da0 = descA0 + (uint64_t)((kb * GP_KB_BYTES) >> 4);
             const uint64_t dw0 = descW0 + (uint64_t)((stage * TK_WST_BYTES) >> 4);
             if (ptx::elect_one()) {
+              const long long ti0 = tm ? clock64() : 0;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 if (p.dbg & 2) break;
@@ -291,11 +295,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
                   ptx::umma_bf16(dbase + 64, da, dw + (uint64_t)((64 * 128) >> 4), id128, 1u);
                 }
               }
+              const long long ti1 = tm ? clock64() : 0;
               ptx::umma_commit(&w_empty[stage]);
               if (ci == nch - 1 && nxt) ptx::umma_commit(&a_free[kb]);
+              if (tm) { w_is += ti1 - ti0; w_cm += clock64() - ti1; }
             }
-            __syncwarp();
+            if (!(p.dbg & 8)) __syncwarp();
             if (++stage == TK_WSTAGES) { stage = 0; phase ^= 1; }
+            if (tm) w_kb += clock64() - tk0;
           }
           if (ptx::elect_one()) {
             if (kind == PH_A || kind == PH_BX) ptx::umma_commit(&tmem_full[b]);
@@ -306,9 +313,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         }
         if (reload) ++n_load;
       }
-      if (tm && lane == 0) {
+      if (p.timing != nullptr && lane == 0) {
         unsigned long long* o = p.timing + (long long)blockIdx.x * 16;
-        o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_te; o[2] = w_af; o[3] = w_wf; o[4] = w_lg;
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        o[5] = gt1 - gt0;   // ns: with o[0], the SM clock the kernel actually ran at
+        o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_te; o[2] = w_af; o[3] = w_wf; o[4] = w_lg; o[13] = w_is; o[14] = w_cm; o[15] = w_kb;
       }
     } else if (warp == 2) {
       // ===================== store warp: staging tile -> history slot / layer output, then the exchange signal ======
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
       if (lane == 0) {
         int n_load = 0;
         unsigned prev_key = 0xffffffffu;
-        const bool tm = p.timing != nullptr;
+        const bool tm = p.timing != nullptr && (p.dbg & 16);
         long long w_fr = 0, w_ex = 0;
         int kind, t;
         for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
@@ -419,7 +429,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
     const uint32_t sw = (uint32_t)(row & 7);
     const long long astride = (long long)vpr * 128;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool tm = p.timing != nullptr && threadIdx.x == 128;
+    const bool tmt = p.timing != nullptr && threadIdx.x == 128;   // trace stamps of one thread
+    const bool tm = tmt && (p.dbg & 16);
     long long w_tf = 0, w_sf = 0, w_lf = 0, w_hp = 0;
     const long long te0 = clock64();
     int n_full[2] = {0, 0};   // tmem_full phases consumed per buffer
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
             }
         }
         load_hp(p.hseq0, E0, t, c, hp);
-        if (tm) tr(1, t - 1, 16 + ci * 4);       // L0(t) is traced with tick t-1 (it follows V(t-1))
+        if (tmt) tr(1, t - 1, 16 + ci * 4);       // L0(t) is traced with tick t-1 (it follows V(t-1))
         uint2 mk[2] = {make_uint2(0x01010101u, 0x01010101u), make_uint2(0x01010101u, 0x01010101u)};
         if (masked) {
           const unsigned char* mp = p.mask + (R0 + row) * H + c * 64 + sub * 16;
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         wait_acc(&tmem_full[b], (uint32_t)(n_full[b] & 1), tm, w_tf);
         ++n_full[b];
         ptx::tc_fence_after();
-        if (tm) tr(1, t - 1, 16 + ci * 4 + 1);
+        if (tmt) tr(1, t - 1, 16 + ci * 4 + 1);
         const uint32_t tacc = tlane + (uint32_t)(b * 256 + sub * 16);
         uint4* gp = SAVE ? p.gates0 + ((rt * GP_GATE_ARRAYS) * vpr + c * 8 + sub * 2) * 128 + row : nullptr;
         uint4 hpk[2], ypk[2];
@@ -526,10 +537,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[b]);
-        if (tm) tr(1, t - 1, 16 + ci * 4 + 2);
+        if (tmt) tr(1, t - 1, 16 + ci * 4 + 2);
         if (masked) stage_tile(ypk[0], ypk[1]);   // y0 first: layer 1 of this tick waits for it
         stage_tile(hpk[0], hpk[1]);
-        if (tm) tr(1, t - 1, 16 + ci * 4 + 3);
+        if (tmt) tr(1, t - 1, 16 + ci * 4 + 3);
       }
     };
 
@@ -541,11 +552,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         const int c = c_lo + ci, b = ci;
         uint4 hp[2];
         load_hp(p.hseq1, E1, t, c, hp);
-        if (tm) tr(1, t, ci * 4);
+        if (tmt) tr(1, t, ci * 4);
         wait_acc(&tmem_full[b], (uint32_t)(n_full[b] & 1), tm, w_tf);
         ++n_full[b];
         ptx::tc_fence_after();
-        if (tm) tr(1, t, ci * 4 + 1);
+        if (tmt) tr(1, t, ci * 4 + 1);
         const uint32_t tacc = tlane + (uint32_t)(b * 256 + sub * 16);   // [n_x | r | z | n_h] x 64
         uint4* gp = SAVE ? p.gates1 + ((rt * GP_GATE_ARRAYS) * vpr + c * 8 + sub * 2) * 128 + row : nullptr;
         uint4 hpk[2];
@@ -585,9 +596,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[b]);
-        if (tm) tr(1, t, ci * 4 + 2);
+        if (tmt) tr(1, t, ci * 4 + 2);
         stage_tile(hpk[0], hpk[1]);
-        if (tm) tr(1, t, ci * 4 + 3);
+        if (tmt) tr(1, t, ci * 4 + 3);
       }
     };
 
@@ -595,7 +606,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
     auto v_epilogue = [&](int t) {
       wait_acc(lg_full, (uint32_t)(t & 1), tm, w_lf);
       ptx::tc_fence_after();
-      if (tm) tr(1, t, 8);
+      if (tmt) tr(1, t, 8);
       float a[16];
       ptx::tmem_ld16(tlane + (uint32_t)(192 + sub * 16), a);
       ptx::tmem_ld_wait();
@@ -635,7 +646,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
       }
       if (bi == 0x7fffffff) bi = 0;
       tokv = bi;
-      if (tm) tr(1, t, 9);
+      if (tmt) tr(1, t, 9);
       if (crank == 0 && sub == 0) {
         if (p.samples != nullptr) p.samples[map_row(p.smap, rbase + row) + t] = bi;
         if (t + 1 < NT) {
@@ -673,13 +684,17 @@ int gru_fold_table(const float* table, long long ld_table, int rows, const float
 
 static bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
-// one launch covers the decode when every CTA of the 4-per-tile grid is co-resident (a 4-CTA cluster grid places 132)
+// Row tiles are independent, so a batch beyond one wave (a 4-CTA cluster grid places 132 CTAs = 33 tiles) could run as
+// successive waves of clusters inside the same launch -- measured at 32768 rows (an inpainting batch): 11.0 ms, the
+// same as the per-tick launches, whose full-width kernels are the better shape once latency no longer matters.  So the
+// default takes this path up to one wave; IPN_TICK_PERSIST_MAXB moves the limit.
 bool tick_persist_shape_ok(const IpnTickDecode* p) {
   const int on = getenv("IPN_TICK_PERSIST") ? atoi(getenv("IPN_TICK_PERSIST")) : 1;   // read per call: tests switch it
   if (!on || !persist_enabled()) return false;
   if (p->core != IPN_CORE_UMMA || p->act_dt != IPN_BF16) return false;
   if (p->H != 256 && p->H != 512) return false;
-  if (p->B <= 0 || p->B % GP_ROWS != 0 || (p->B / GP_ROWS) * TK_CS > 132) return false;
+  const long long maxb = getenv("IPN_TICK_PERSIST_MAXB") ? atoll(getenv("IPN_TICK_PERSIST_MAXB")) : 33LL * GP_ROWS;
+  if (p->B <= 0 || p->B % GP_ROWS != 0 || p->B > maxb) return false;
   if (p->V <= 0 || p->V > 64) return false;
   const IpnGruDir& A = p->l0;
   const IpnGruDir& Bd = p->l1;

@@ -15,8 +15,8 @@ m.decoder.teacher_forcing_prob = -1.0
 tok = torch.randint(0, V, (B, 24)).to(DEV)
 ncta = B // 128 * 4
 timing = torch.zeros(4096 * 16, dtype=torch.int64, device=DEV)
-names = ["mma_total", "mma_wait_tmem_empty", "mma_wait_a_full", "mma_wait_w_full", "mma_wait_lg_empty", "-", "aload_wait_a_free",
-         "aload_wait_exchange", "epi_total", "epi_wait_tmem_full", "epi_wait_stg_free", "epi_wait_lg_full", "epi_wait_hp"]
+names = ["mma_total", "mma_wait_tmem_empty", "mma_wait_a_full", "mma_wait_w_full", "mma_wait_lg_empty", "mma_total_ns (globaltimer)", "aload_wait_a_free",
+         "aload_wait_exchange", "epi_total", "epi_wait_tmem_full", "epi_wait_stg_free", "epi_wait_lg_full", "epi_wait_hp", "mma_issue (elected lane)", "mma_commit (elected lane)", "mma k-block iterations, all"]
 for train in (False, True):
     m.train(train)
     for it in range(3):
@@ -34,7 +34,7 @@ for train in (False, True):
     mean, mx = t.mean(0).cpu().tolist(), t.max(0).values.cpu().tolist()
     print(f"train={train}: per CTA, kcycles for 24 ticks (mean / max over {ncta} CTAs)")
     for i, n in enumerate(names):
-        if n != "-":
+        if n != "-" and mean[i] > 0:
             print(f"   {n:22s} {mean[i] / 1e3:9.1f} {mx[i] / 1e3:9.1f}   per tick {mean[i] / 24e3:7.2f}")
     # timeline of cluster 0 / rank 0, ticks 8 and 9 (cycle stamps; role 0 MMA, 1 epilogue thread 128, 2 store warp, 3 A loader)
     PH = ["A(t+1)", "Bh(t+1)", "Bx(t)", "V(t)"]
