@@ -362,7 +362,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaBatch<Epi> batch) {
 // =============================================================================================
 template <int BR_, bool TW_, bool TX_, bool PAIR_ = false>
 struct UmmaPCfg {
-  static constexpr int EPI_WARPS = 8;
+#ifndef IPN_PGEMM_EPI_WARPS
+#define IPN_PGEMM_EPI_WARPS 16
+#endif
+  static constexpr int EPI_WARPS = IPN_PGEMM_EPI_WARPS;   // 4 per TMEM lane quadrant: the epilogue of K <= 1024 products is latency bound
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int PARTS = EPI_WARPS / 4;
   static constexpr int G = 1;
