@@ -295,6 +295,24 @@ __global__ void pack_bf16_kernel(const IpnPackItem* items) {
   const IpnPackItem it = items[blockIdx.y];
   const long long total = (long long)it.rows * it.ld_dst;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it.dst);
+  // fast path (every large matrix): 8 elements per thread, two 16-byte loads -> one 16-byte store, 32-bit index math
+  if ((it.cols & 7) == 0 && (it.ld_dst & 7) == 0 && (it.ld_src & 3) == 0 && total < (1LL << 31) &&
+      (reinterpret_cast<uintptr_t>(it.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(it.dst) & 15) == 0) {
+    const unsigned vpr = (unsigned)it.ld_dst >> 3, nvec = (unsigned)(total >> 3), cv = (unsigned)it.cols >> 3;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+      const unsigned r = i / vpr, c = i - r * vpr;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (c < cv) {
+        const float4* sp = reinterpret_cast<const float4*>(it.src + (long long)r * it.ld_src + c * 8);
+        const float4 a = sp[0], b = sp[1];
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+        h2[0] = __floats2bfloat162_rn(a.x, a.y); h2[1] = __floats2bfloat162_rn(a.z, a.w);
+        h2[2] = __floats2bfloat162_rn(b.x, b.y); h2[3] = __floats2bfloat162_rn(b.z, b.w);
+      }
+      reinterpret_cast<uint4*>(dst)[i] = o;
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / it.ld_dst;
     const int c = (int)(i % it.ld_dst);
@@ -584,7 +602,7 @@ int ipn_pack_bf16(const IpnPackItem* items_dev, int n, int max_rows, int max_ld_
   ProfScope prof("pack_bf16", 0.0, (double)(0), STREAM);
   IPN_REQUIRE(items_dev && n > 0, IPN_ERR_ARG, "pack_bf16: bad args");
   const long long total = (long long)max_rows * max_ld_dst;
-  dim3 grid((unsigned)imin(64, cdiv(total, 256)), n);
+  dim3 grid((unsigned)imin(96, cdiv(total, 8 * 256)), n);
   pack_bf16_kernel<<<grid, 256, 0, STREAM>>>(items_dev);
   IPN_LAUNCH_CHECK();
   return IPN_OK;
