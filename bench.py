@@ -699,7 +699,7 @@ def main():
         value = world * B * K / (ms / 1e3)
         e2e_value = world * B * K / (ms_e2e / 1e3)
         kernels = mv["kernels"]
-        roofline, crit = cx.rooflines(kernels, critical=("gru_layer_fwd_persist", "gru_layer_bwd_persist"))
+        roofline, crit = cx.rooflines(kernels, critical=("gru_layer_fwd_persist", "gru_layer_bwd_persist", "tick_decode_persist"))
         if roofline is not None:
             roofline["standalone"] = mv["standalone"]
             roofline["note"] = ("achieved = in-step launch durations (side stream, next to chain kernels that hold 128 SMs); "
@@ -707,6 +707,11 @@ def main():
         # the serial chain: per-step latency of one encoder-layer step against the floors of DESIGN.md section 4.3
         # (12.9 GFLOP at the sustained tensor peak; 84 MB of algorithmic bytes at the measured HBM rate)
         for c in crit:
+            if c["kernel"] == "tick_decode_persist":
+                c["floor_note"] = ("argmax decode, 24 serial ticks of 4096 measures in one launch: 0.47 TFLOP -> %.0f us at the tensor "
+                                   "peak; a tick is a chain of 4 MMA phases, 3 epilogues and 2 cluster exchanges (DESIGN.md section 4.5)"
+                                   % (0.47e12 / (cx.tf_peak * 1e12) * 1e6))
+                continue
             c["floor_note"] = ("encoder layer step at B=4096, both directions: 12.9 GFLOP -> %.1f us at the tensor peak; 84 MB "
                                "algorithmic bytes -> %.1f us at the HBM peak" % (12.9e9 / (cx.tf_peak * 1e12) * 1e6,
                                                                                 84e6 / (cx.hbm_peak * 1e9) * 1e6))
