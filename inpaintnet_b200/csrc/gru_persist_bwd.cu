@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) gru_prep_dy_kernel(PrepDY p) {
 }
 
 constexpr int GPB_A_STAGES = 3;        // A k-blocks are re-read from L2 (latency ~1.5 kcycles): 2 stages starve the MMAs
-constexpr int GPB_W_RING = 80 * 1024;
+constexpr int GPB_W_RING = 112 * 1024;   // 3 stages of a 32 KB column-split stage (2 starve the MMAs: the ring round trip is ~2.8 kcycles); all the shared memory there is
 constexpr int GPB_NBAR = 48;
 static inline int gpb_smem_bytes() { return GPB_A_STAGES * GP_KB_BYTES + GPB_W_RING + 4 * GP_KB_BYTES + GPB_NBAR * 8 + 16; }
 
@@ -65,7 +65,7 @@ static inline int gpb_smem_bytes() { return GPB_A_STAGES * GP_KB_BYTES + GPB_W_R
 // TMA-stores its chunks as before and signals the PEER's dg_stored barrier once the store has completed.
 template <bool PAIR, int CS>
 __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __grid_constant__ GruPersistBwd p) {
-  static_assert(CS == 1 || (CS == 2 && !PAIR), "column split uses plain (cta_group::1) MMAs");
+  static_assert(CS == 1 || CS == 2, "column split: 2 CTAs per tile, or 2 CTA pairs per two tiles");
   extern __shared__ __align__(1024) uint8_t smem[];
   const GruPersistBwdDir& D = p.d[blockIdx.y];
   const int H = p.H, KB = H >> 6, T = p.T, Bt = p.Bt;
@@ -73,13 +73,18 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
   const int NPH = H / NH;                // columns per MMA
   const int WSTB = p.nbs * 8192;         // bytes of one W stage in this CTA
   const int WSTAGES = min(6, GPB_W_RING / WSTB);
-  const int rbase = (CS > 1 ? (int)blockIdx.x / CS : (int)blockIdx.x) * GP_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = (PAIR || CS > 1) ? ptx::cluster_ctarank() : 0u;
-  const uint32_t rank = PAIR ? crank : 0u;
+  const uint32_t rank = PAIR ? (crank & 1u) : 0u;   // pair: which 128 rows of the M = 256 tile / which half of every W stage
   const bool leader = rank == 0;
-  const int h_lo = CS > 1 ? (int)crank : 0, h_hi = CS > 1 ? h_lo + 1 : NH;               // accumulator halves of this CTA
-  const int c_lo = CS > 1 ? (int)crank * (KB / CS) : 0, c_hi = c_lo + KB / CS;          // 64-unit chunks of this CTA
+  const uint32_t lead_rank = crank & ~1u;           // cluster rank of this pair's leader CTA
+  const uint16_t pair_mask = (uint16_t)(3u << lead_rank);
+  // PAIR + CS = 2 (as in the forward kernel): a cluster of 4 = two pairs, pair `crank >> 1` owns one 256-column half
+  // of dh for TWO adjacent row tiles; each CTA stages half of every W stage, so the ring holds twice as many
+  const uint32_t colrank = PAIR ? (crank >> 1) : crank;
+  const int rbase = (PAIR ? ((int)blockIdx.x / (2 * CS)) * 2 + (int)rank : (int)blockIdx.x / CS) * GP_ROWS;
+  const int h_lo = CS > 1 ? (int)colrank : 0, h_hi = CS > 1 ? h_lo + 1 : NH;            // accumulator halves of this CTA
+  const int c_lo = CS > 1 ? (int)colrank * (KB / CS) : 0, c_hi = c_lo + KB / CS;        // 64-unit chunks of this CTA
   const int nM = D.dh0 != nullptr ? T : T - 1;   // number of GEMM phases (the last one only feeds dh0)
 
   uint8_t* sA = smem;
@@ -190,21 +195,21 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
                 if (PAIR) ptx::umma_bf16_pair(dcol, da0 + (uint64_t)(kk * 2), dw0 + (uint64_t)(kk * 128), idesc, 1u);
                 else ptx::umma_bf16(dcol, da0 + (uint64_t)(kk * 2), dw0 + (uint64_t)(kk * 128), idesc, 1u);
               }
-              if (PAIR) ptx::umma_commit_pair(&w_empty[ws]);
+              if (PAIR) ptx::umma_commit_pair(&w_empty[ws], pair_mask);
               else ptx::umma_commit(&w_empty[ws]);
             }
             __syncwarp();
             if (++ws == WSTAGES) { ws = 0; wph ^= 1; }
           }
           if (ptx::elect_one()) {
-            if (PAIR) ptx::umma_commit_pair(&a_empty[as]);
+            if (PAIR) ptx::umma_commit_pair(&a_empty[as], pair_mask);
             else ptx::umma_commit(&a_empty[as]);
           }
           __syncwarp();
           if (++as == GPB_A_STAGES) { as = 0; aph ^= 1; }
         }
         if (ptx::elect_one()) {
-          if (PAIR) ptx::umma_commit_pair(tmem_full);
+          if (PAIR) ptx::umma_commit_pair(tmem_full, pair_mask);
           else ptx::umma_commit(tmem_full);
         }
         __syncwarp();
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
             uint64_t* ds = (it & 1) ? &dg_stored_odd[c] : &dg_stored[c];
             ptx::mbar_arrive(ds);
             ptx::fence_acq_rel_cluster();
-            ptx::mbar_arrive_remote_relaxed(ds, crank ^ 1u);
+            ptx::mbar_arrive_remote_relaxed(ds, PAIR ? (crank ^ 2u) : (crank ^ 1u));   // same rows, the other half of dh
           } else {
             ptx::mbar_arrive(&dg_stored[c]);
           }
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       __syncwarp();
       if (lane == 0) {
         if (leader) ptx::mbar_arrive(tmem_free);
-        else ptx::mbar_arrive_remote(tmem_free, 0);
+        else ptx::mbar_arrive_remote(tmem_free, lead_rank);
       }
     }
     if (D.dh0 != nullptr) {
@@ -443,7 +448,12 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
   // column split (kernel header comment): on unless IPN_GPB_CS=0
   static const int cs_on = getenv("IPN_GPB_CS") ? atoi(getenv("IPN_GPB_CS")) : 1;
   const bool cs = cs_on && NH == 2 && 2 * (Bt / GP_ROWS) * L->ndir <= 148;
-  const bool pair = !cs && pair_on && (Bt / GP_ROWS) % 2 == 0 && NPH % 128 == 0;
+  // CTA pairs inside the column split: opt-in (IPN_GPB_PAIRCS=1).  Unlike the forward kernel it measured SLOWER here
+  // (layer backward 4.84 vs 4.35 ms per two train steps) once the W ring holds 3 full stages: the pair couples two
+  // row tiles' E phases, and the streamed A operand already keeps the per-stage MMA work at 684 cycles.
+  static const int paircs_on = getenv("IPN_GPB_PAIRCS") ? atoi(getenv("IPN_GPB_PAIRCS")) : 0;
+  const bool pair = pair_on && (Bt / GP_ROWS) % 2 == 0 && NPH % 128 == 0 &&
+                    (!cs || (paircs_on && 2 * (Bt / GP_ROWS) * L->ndir <= 132));
   if (cs) p.timing = nullptr;   // the diagnostics buffer is sized for one CTA per tile
   p.nbs = pair ? NPH / 128 : NPH / 64;
   const long long per_dir = (long long)T * Bt * H * 2;
@@ -489,7 +499,7 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (pair || cs) ? 2 : 1;
+    attr[0].val.clusterDim.x = (pair && cs) ? 4 : (pair || cs) ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -498,8 +508,9 @@ int gru_persist_bwd(const IpnGruLayerBwd* L, void* ws, long long ws_bytes, cudaS
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[3] = {false, false, false};
-  if (cs) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false, 2>, &cfgd[2]));
+  static bool cfgd[4] = {false, false, false, false};
+  if (cs && pair) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<true, 2>, &cfgd[3]));
+  else if (cs) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false, 2>, &cfgd[2]));
   else if (pair) IPN_PROPAGATE(launch(gru_persist_bwd_kernel<true, 1>, &cfgd[0]));
   else IPN_PROPAGATE(launch(gru_persist_bwd_kernel<false, 1>, &cfgd[1]));
   return IPN_OK;
