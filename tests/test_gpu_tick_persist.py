@@ -21,14 +21,14 @@ from tests.golden import recipe
 from tests.test_gpu_fullsize import _lib_masks, rel_err
 
 DEV = "cuda"
-H, Z = 512, 256
+Z = 256
 
 
-def _decode(sd, V, B, train, persist, seed=29):
+def _decode(sd, V, H, B, train, persist, seed=29):
     old = os.environ.get("IPN_TICK_PERSIST")
     os.environ["IPN_TICK_PERSIST"] = "1" if persist else "0"
     try:
-        m = MeasureVAE(SyntheticFolkDataset(num_notes=V))
+        m = MeasureVAE(SyntheticFolkDataset(num_notes=V), encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
         m.load_state_dict(sd)
         m.to(DEV).set_precision("bf16")
         m.train(train)
@@ -69,16 +69,16 @@ def _oracle_along(sd, r, rows, train):
 
 
 @pytest.mark.parametrize("train", [False, True])
-@pytest.mark.parametrize("V", [64, 47])
-def test_persistent_tick_decode_matches_per_tick_path_and_oracle(V, train):
+@pytest.mark.parametrize("V,H", [(64, 512), (47, 512), (64, 256)])   # H = 256: one 64-unit chunk per CTA of the cluster
+def test_persistent_tick_decode_matches_per_tick_path_and_oracle(V, H, train):
     B = 256
     sd = recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), 4321)
-    a = _decode(sd, V, B, train, persist=True)
-    b = _decode(sd, V, B, train, persist=False)
+    a = _decode(sd, V, H, B, train, persist=True)
+    b = _decode(sd, V, H, B, train, persist=False)
     # one launch (+ the table fold) instead of 24 x 5
     assert a["launches"] + 100 < b["launches"], (a["launches"], b["launches"])
     same = (a["s"] == b["s"]).all(2).all(1)
-    print(f"tick decode V={V} train={train}: launches {b['launches']} -> {a['launches']}; token paths equal on "
+    print(f"tick decode V={V} H={H} train={train}: launches {b['launches']} -> {a['launches']}; token paths equal on "
           f"{same.float().mean().item():.3f} of the measures, tokens equal {(a['s'] == b['s']).float().mean().item():.4f}")
     assert same.float().mean().item() > 0.8
     # same token path => same inputs at every tick; the layer-1 input product stays in fp32 (TMEM) in the persistent
