@@ -70,9 +70,26 @@ def test_forward_backward_vs_reference_golden(name, prec, mode):
     same_path = torch.equal(s_lib, g["samples"])
     if same_path:
         assert rel_err(weights.detach().cpu(), g["weights"]) < tol
-    else:  # bf16 argmax: token feedback may legitimately diverge after a near-tie; report the agreement
+    else:
+        # bf16 argmax: the token feedback may legitimately leave the reference's path -- but only AT a near-tie of the
+        # reference's own logits.  Per measure: up to and including the first differing tick the logits must match
+        # within the tolerance (same inputs so far), and at that tick the reference's top-1 margin must be small.
+        gs, gw, w_lib = g["samples"][:, 0], g["weights"], weights.detach().cpu()
+        diff = s_lib[:, 0] != gs
+        n_div = 0
+        for b in range(gs.shape[0]):
+            if not bool(diff[b].any()):
+                assert rel_err(w_lib[b], gw[b]) < tol
+                continue
+            n_div += 1
+            t0 = int(diff[b].float().argmax())
+            assert rel_err(w_lib[b, :t0 + 1], gw[b, :t0 + 1]) < tol, (b, t0)
+            top2 = gw[b, t0].topk(2).values
+            assert float(top2[0] - top2[1]) < 5e-2 * float(gw[b].abs().max().clamp_min(1e-6)), (b, t0, top2)
         agree = (s_lib == g["samples"]).float().mean().item()
-        assert agree > 0.5, agree
+        print(f"bf16 argmax [{name}]: {n_div}/{gs.shape[0]} measures leave the reference token path at a near-tie; "
+              f"token agreement {agree:.3f}")
+        assert agree > 0.9, agree   # measured: 0.986 (mvae_h64: 1 of 6 measures diverges, at a near-tie); mvae_default stays on the path
         return
     loss, acc = Fn.fused_ce_kl(weights, tokens, z_dist.loc, z_dist.log_std, beta=0.001)
     assert abs(loss.item() - g["loss"]) < (2e-4 if prec == "fp32" else 2e-2)
