@@ -394,6 +394,10 @@ int ipn_dlogits_relayout_mapped(const float* dweights, const float* weights, int
  * Buffers use the decoder row order: slot j (tick within beat) x 4B rows (i*B + b).
  * l0/l1 describe the two layers as for ipn_gru_layer_fwd (T = 6, B_total = 4B); l0.tok must point to
  * `tokprev` whose rows [0,B) the caller has set to V (the x_0 row of the table).
+ * With a workspace (ws), bf16, H in {256, 512}, V <= 64, B a multiple of 128 up to 4224, and layer 0 in the
+ * two-term form (blocked broadcast P + token table) the whole decode is ONE persistent kernel launch
+ * (csrc/tick_persist.cu); `Pt1` is then not written (the layer-1 input product never leaves tensor memory).
+ * Otherwise: 5 launches per tick.  Same outputs and saved state either way.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int core, act_dt;
