@@ -249,18 +249,23 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
     eps_* (B,n,Z): injected rsample noise (latent_rnn.py:172 samples even in eval).
     Returns weights (B,n_gen,24,V), samples (B,1,24*n_gen), z_out (B,n_gen,Z).
     The target-encode of latent_rnn.py:133 does not influence any output in this mode.
+    Train-mode dropout (keep masks, 1 = keep): ctx_keep_masks = {"past": [(B,np,2Hc)], "future": [(B,nf,2Hc)]},
+    gen_keep_masks = [(B,n_gen,2Hg)] with dropout_p; vae_dropout = {"enc_past": (B*np,24,2H), "enc_future":
+    (B*nf,24,2H), "dec": [(beat (B,4,H), tick (B,24,H)) per gap measure]} with vae_dropout_p.
     fed_tokens (B,n_gen,24): test hook -- decode with THESE tokens fed back instead of the oracle's own argmax (no
     gradient flows through the argmax, so this is the same function of the parameters along a given token path).
     only="past"/"future": LatentRNNAblations (latent_rnn_ablations.py:143-146), one context seeds the generation GRU."""
     B = past.shape[0]
     vp = "vae_model."
+    vd = vae_dropout or {}     # train mode recurses into the frozen VAE (utils/trainer.py:78): its dropout is active too
 
-    def z_seq(m, eps):                                                         # latent_rnn.py:161-174
+    def z_seq(m, eps, keep):                                                   # latent_rnn.py:161-174
         n = m.shape[1]
-        mu, ls = encoder_forward(sd, m.reshape(-1, 24), 2, None, 0.0, prefix=vp + "encoder.")
+        mu, ls = encoder_forward(sd, m.reshape(-1, 24), 2, [keep] if keep is not None else None,
+                                 vae_dropout_p if keep is not None else 0.0, prefix=vp + "encoder.")
         return (mu + torch.exp(ls) * eps.reshape(-1, eps.shape[-1])).view(B, n, -1)
 
-    zp, zf = z_seq(past, eps_past), z_seq(future, eps_future)
+    zp, zf = z_seq(past, eps_past, vd.get("enc_past")), z_seq(future, eps_future, vd.get("enc_future"))
     Hc = sd["context_rnn_past.weight_hh_l0"].shape[1]
     h0 = torch.zeros(num_layers * 2, B, Hc, dtype=zp.dtype)
     km = ctx_keep_masks or {}
@@ -273,10 +278,12 @@ def latent_rnn_forward(sd, past, future, target, n_gen, eps_past, eps_future, nu
                    sd["generation_linear.bias"]).view(B, n_gen, -1)           # latent_rnn.py:232-233
     ws, ss = [], []
     for i in range(n_gen):                                                     # latent_rnn.py:237-240
+        bm, tm = vd["dec"][i] if "dec" in vd else (None, None)
+        dkw = dict(beat_keep_masks=[bm], tick_keep_mask=tm, dropout_p=vae_dropout_p) if bm is not None else {}
         if fed_tokens is None:
-            w, s = decoder_forward(sd, z_out[:, i], None, False, 2, prefix=vp + "decoder.")
+            w, s = decoder_forward(sd, z_out[:, i], None, False, 2, prefix=vp + "decoder.", **dkw)
         else:
-            w, s = decoder_forward(sd, z_out[:, i], fed_tokens[:, i], True, 2, prefix=vp + "decoder.")
+            w, s = decoder_forward(sd, z_out[:, i], fed_tokens[:, i], True, 2, prefix=vp + "decoder.", **dkw)
         ws.append(w)
         ss.append(s)
     return torch.stack(ws, 1), torch.cat(ss, 2), z_out

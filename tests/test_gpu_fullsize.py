@@ -162,6 +162,74 @@ def test_latent_rnn_train_step_full_size(prec):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_latent_rnn_train_mode_dropout_masks_injected(prec):
+    """LatentRNN (auto_reg=False) in TRAIN mode: dropout is active in the context GRUs, the generation GRU AND the frozen
+    MeasureVAE's encoder and decoder (utils/trainer.py:78 recurses).  The oracle's placement of all of them is pinned to
+    the unmodified reference by tests/test_oracle_dropout_placement.py; here the CUDA path gets the same keep-masks
+    injected (library layouts, consumption order: VAE encoder over all context measures, past / future context GRU,
+    generation GRU, decoder beat + tick) and must reproduce latents, logits and every trainable gradient."""
+    from inpaintnet_b200.latent_rnn import LatentRNN
+    V, H, Z, Hc, S, p = 64, 512, 256, 512, 128, 0.5
+    n_p, n_t, n_f = 3, 2, 3
+    sd = recipe.make_state_dict(recipe.latent_rnn_spec(Z, Hc), 177)
+    sd.update({"vae_model." + k: v for k, v in recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), 178).items()})
+    ds = SyntheticFolkDataset(num_notes=V)
+    m = LatentRNN(ds, MeasureVAE(ds), 2, Hc, p, torch.nn.GRU, auto_reg=False)
+    m.load_state_dict(sd)
+    m.to(DEV).set_precision(prec)
+    m.train()
+    assert m.vae_model.encoder.training and m.vae_model.decoder.training
+    g = torch.Generator().manual_seed(41)
+    score = torch.randint(0, V, (S, n_p + n_t + n_f, 24), generator=g)
+    past, target, future = (x.contiguous() for x in (score[:, :n_p], score[:, n_p:n_p + n_t], score[:, n_p + n_t:]))
+    eps_p, eps_f = torch.randn(S, n_p, Z, generator=g), torch.randn(S, n_f, Z, generator=g)
+    keep = lambda *shape: (torch.rand(*shape, generator=g) > p)
+    enc_p, enc_f = keep(S, n_p, 24, 2 * H), keep(S, n_f, 24, 2 * H)            # [b, m, t, :]
+    ctx_p, ctx_f, gen = keep(S, n_p, 2 * Hc), keep(S, n_f, 2 * Hc), keep(S, n_t, 4 * Hc)
+    dec_beat, dec_tick = keep(n_t, S, 4, H), keep(n_t, S, 24, H)               # [gap measure, b, ...]
+    # ---- library layouts, in the order the engine consumes them
+    u8 = lambda x: x.to(torch.uint8).contiguous()
+    tm = lambda x: x.transpose(0, 1).reshape(-1, x.shape[-1])                   # (b, m, C) -> rows m*S + b
+    enc_lib = torch.cat([enc_p.permute(2, 1, 0, 3), enc_f.permute(2, 1, 0, 3)], 1).reshape(24 * (n_p + n_f) * S, 2 * H)
+    Bd = n_t * S                                                                # decoder rows i*S + b
+    beat_lib = dec_beat.reshape(Bd, 4, H).transpose(0, 1).reshape(4 * Bd, H)
+    tick_lib = dec_tick.reshape(Bd, 4, 6, H).permute(2, 1, 0, 3).reshape(24 * Bd, H)
+    masks = [u8(enc_lib), u8(tm(ctx_p)), u8(tm(ctx_f)), u8(tm(gen)), u8(beat_lib), u8(tick_lib)]
+    eps = [eps_p.transpose(0, 1).reshape(n_p * S, Z), eps_f.transpose(0, 1).reshape(n_f * S, Z)]
+    rows = torch.tensor([0, 1, S // 2, S - 1])
+    m.zero_grad()
+    with engine.inject_noise(masks=masks, eps=eps):
+        w, s, gz = m(past.to(DEV), future.to(DEV), target.to(DEV), n_t, train=True)
+    rd = rows.to(DEV)
+    loss = torch.nn.functional.cross_entropy(w[rd].reshape(-1, V), target.to(DEV)[rd].reshape(-1))
+    loss.backward()
+    torch.cuda.synchronize()
+    # ---- oracle on the picked sequences with the same masks, decoding along the GPU run's token path
+    sdr = {k: (v.clone().requires_grad_() if not k.startswith("vae_model.") else v.clone()) for k, v in sd.items()}
+    f = lambda x: x[rows].float()
+    fed = s.cpu()[rows, 0].view(len(rows), n_t, 24)
+    vd = dict(enc_past=f(enc_p).reshape(-1, 24, 2 * H), enc_future=f(enc_f).reshape(-1, 24, 2 * H),
+              dec=[(dec_beat[i][rows].float(), dec_tick[i][rows].float()) for i in range(n_t)])
+    w_r, _, z_r = O.latent_rnn_forward(sdr, past[rows], future[rows], target[rows], n_t, eps_p[rows], eps_f[rows],
+                                       ctx_keep_masks=dict(past=[f(ctx_p)], future=[f(ctx_f)]), gen_keep_masks=[f(gen)],
+                                       dropout_p=p, vae_dropout=vd, vae_dropout_p=p, fed_tokens=fed)
+    tol = 1e-3 if prec == "fp32" else 2e-2
+    assert rel_err(gz.detach().cpu()[rows], z_r.detach()) < tol
+    top2 = w_r.detach().topk(2, dim=3).values
+    strict = (top2[..., 0] - top2[..., 1]) > (1e-4 if prec == "fp32" else 5e-2)
+    assert bool(((w_r.detach().argmax(3) == fed) | ~strict).all()), "fed-back token is not the argmax on a strict-margin row"
+    assert rel_err(w.detach().cpu()[rows], w_r.detach()) < tol
+    O.mean_crossentropy_loss(w_r, target[rows]).backward()
+    ref = {k: v.grad for k, v in sdr.items() if v.requires_grad}
+    errs = grad_errs(m.named_parameters(), ref)
+    assert len(errs) == len(ref) and errs
+    lim = 3e-3 if prec == "fp32" else 0.15
+    print(f"latent train-mode dropout [{prec}]: max grad err {max(errs.values()):.3e} ({max(errs, key=errs.get)})")
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < lim}
+    assert not bad, bad
+
+
 def _arnn(V, prec, sd=None):
     from inpaintnet_b200.arnn import ConstraintModelGaussianReg
     ds = SyntheticFolkDataset(num_notes=V)
