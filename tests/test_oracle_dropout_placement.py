@@ -118,3 +118,35 @@ def test_latent_rnn_train_mode_dropout_replayed_from_the_reference_generator():
     assert torch.allclose(z2, gz, atol=5e-6, rtol=1e-5)
     assert torch.equal(s2, s)
     assert torch.allclose(w2.reshape(w.shape), w, atol=1e-5, rtol=1e-5)
+
+
+def test_arnn_train_mode_input_dropout_replayed_from_the_reference_generator():
+    """AnticipationRNN, teacher forced, train mode: the only dropout the reference applies is the whole-timestep input
+    dropout (`nn.Dropout2d` on x[:, :, :, None], arnn_model.py:142,437-442; `lstm_with_activations` is never given its
+    dropout_layer, and the single-layer nn.LSTMs ignore their own `dropout`).  Its noise tensor is (B, T, 1, 1)."""
+    from oracle.ref_import import load_reference, FakeDataset
+    R = load_reference()
+    random.seed(21)
+    torch.manual_seed(21)
+    V, B, T, p = 20, 3, 4 * 24, 0.2
+    m = R.ConstraintModelGaussianReg(
+        dataset=FakeDataset(V), note_embedding_dim=10, metadata_embedding_dim=2, num_lstm_constraints_units=32,
+        num_lstm_generation_units=32, linear_hidden_size=32, num_layers=2, dropout_input_prob=p, dropout_prob=0.2,
+        unary_constraint=True, teacher_forcing=True)
+    m.train()
+    score = torch.randint(0, V, (B, 1, T))
+    t = torch.arange(T)
+    md = torch.stack([(t // 6) % 4 == 0, t % 6, torch.zeros_like(t)], 1).long().view(1, 1, T, 3).expand(B, 1, T, 3).contiguous()
+    cl = torch.ones(B, 1, T).long()
+    cl[:, :, 24:48] = 0
+    torch.manual_seed(77)
+    state = torch.get_rng_state()
+    weights, _ = m._forward_tf(score, md, cl)
+    after = torch.get_rng_state()
+    torch.set_rng_state(state)
+    keep = torch.empty(B, T, 1, 1).bernoulli_(1 - p)[:, :, 0, 0]
+    assert torch.equal(torch.get_rng_state(), after), "the reference consumed the generator in a different order"
+    assert 0 < keep.sum() < keep.numel()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    logits = O.arnn_forward_tf(sd, score, md, cl, 2, keep_input_steps=keep, dropout_input_p=p)
+    assert torch.allclose(logits, weights[0], atol=5e-6, rtol=1e-5)
