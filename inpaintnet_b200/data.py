@@ -4,6 +4,8 @@ out of scope): exposes exactly the dataset surface t
 import torch
 from torch.utils.data import TensorDataset, DataLoader
 
+from . import score as _score
+
 
 class _Metadata:
     def __init__(self, num_values, name):
@@ -24,13 +26,16 @@ class BeatMarkerMetadata(_Metadata):
 
 class SyntheticFolkDataset:
     """Attributes: note2index_dicts[0] (len = V), n_bars, subdivision, num_beats_per_bar, num_voices,
-    metadatas, NOTES, data_loaders(batch_size, split) -> 3 DataLoaders of (score int32 (B,1,L), metadata
+    metadatas, NOTES, tick_values / tick_durations, tensor_to_score, data_loaders(batch_size, split) -> 3 DataLoaders of (score int32 (B,1,L), metadata
     int32 (B,1,L,3)) -- DatasetManager/music_dataset.py:177-221, folk_dataset.py:751-861."""
 
     def __init__(self, num_notes=64, n_bars=16, num_sequences=2048, seed=0, name="folk_4by4nbars_train"):
         self.name = name
-        self.note2index_dicts = [{i: i for i in range(num_notes)}]
-        self.index2note_dicts = [{i: i for i in range(num_notes)}]
+        names = _score.default_vocabulary(num_notes)           # rest, slur, START, END, then pitches from G3 upwards
+        self.note2index_dicts = [{n: i for i, n in enumerate(names)}]
+        self.index2note_dicts = [{i: n for i, n in enumerate(names)}]
+        self.tick_values = list(_score.TICK_VALUES)
+        self.tick_durations = _score.tick_durations(self.tick_values)
         self.n_bars = n_bars
         self.subdivision = 6
         self.num_beats_per_bar = 4
@@ -48,6 +53,13 @@ class SyntheticFolkDataset:
 
     def empty_score_tensor(self, score_length):
         return torch.zeros(self.num_voices, score_length).long()
+
+    def tensor_to_score(self, tensor_score):
+        """Token tensor (any shape, flattened in time order) -> score.Score (folk_dataset.py:472-502 without music21):
+        `dataset.tensor_to_score(samples.cpu()).write("midi", fp=path)` is the reference testers' export call."""
+        slur = self.note2index_dicts[self.NOTES][_score.SLUR_SYMBOL]
+        toks = torch.as_tensor(tensor_score).detach().cpu().reshape(-1).tolist()
+        return _score.tokens_to_score(toks, self.index2note_dicts[self.NOTES], slur, self.tick_durations)
 
     def tensor_dataset(self):
         if self._tensor_dataset is None:

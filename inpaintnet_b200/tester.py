@@ -1,6 +1,7 @@
 """Held-out loss / accuracy loops of the reference testers (MeasureVAE/vae_tester.py:34-49,114-155;
-LatentRNN/latent_rnn_tester.py:28-50,297-340).  Plotting, t-SNE and music21 score export are CPU
-post-processing outside the hot path and are not provided."""
+LatentRNN/latent_rnn_tester.py:28-50,297-340) and the inpainting call that returns scores
+(latent_rnn_tester.py:191-262; scores are `score.Score` objects with MIDI export instead of music21 streams).
+Plotting and t-SNE are CPU post-processing outside the hot path and are not provided."""
 import torch
 
 from . import functional as Fn
@@ -75,6 +76,34 @@ class LatentRNNTester(object):
         if extra_outs:
             return past, future, target, num_past, num_target
         return past, future, target
+
+    def generate(self, tensor_past, tensor_future, tensor_target, num_target_measures=None, eval=False):
+        """latent_rnn_tester.py:191-262: inpaint `num_target_measures` measures between the two contexts
+        ((B, n, 24) token tensors) and return (generated score, generated token tensor (B, n_total, 24), original score
+        or None).  Scores come from `dataset.tensor_to_score` (first sequence of the batch laid out in time, as the
+        reference's flatten does for its batch of one)."""
+        if tensor_target is not None:
+            assert num_target_measures in (None, tensor_target.size(1))
+            num_target_measures = tensor_target.size(1)
+        elif num_target_measures is None:
+            raise ValueError("the number of measures to generate is needed when there is no target")
+        past, future = to_cuda_variable_long(tensor_past), to_cuda_variable_long(tensor_future)
+        target = to_cuda_variable_long(tensor_target) if tensor_target is not None else \
+            torch.zeros(past.size(0), num_target_measures, self.measure_seq_len, dtype=torch.long, device=past.device)
+        with torch.no_grad():
+            weights, gen_target, _ = self.model(past_context=past, future_context=future, target=target,
+                                                measures_to_generate=num_target_measures, train=False)
+            if tensor_target is not None and eval:
+                loss, acc = Fn.fused_ce_kl(weights, target)
+                print('Accuracy for Test Case:')
+                print(f'\tLoss: {to_numpy(loss.mean())}\tAccuracy: {to_numpy(acc) * 100} %')
+        gen_target = gen_target.view(past.size(0), num_target_measures, self.measure_seq_len)
+        gen_score_tensor = torch.cat((past, gen_target, future), 1)
+        gen_score = self.dataset.tensor_to_score(gen_score_tensor[:1].cpu())
+        original_score = None
+        if tensor_target is not None:
+            original_score = self.dataset.tensor_to_score(torch.cat((past, target, future), 1)[:1].cpu())
+        return gen_score, gen_score_tensor, original_score
 
     def test_model(self, batch_size=64):
         (_, _, gen_test) = self.dataset.data_loaders(batch_size=batch_size, split=(0.01, 0.01))

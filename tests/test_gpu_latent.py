@@ -258,3 +258,25 @@ def test_graphed_inpainter_replays_the_eager_call_bit_for_bit():
     gi(score.pin_memory())
     torch.cuda.synchronize()
     assert all(not torch.equal(a, b) for a, b in zip(before, gi.eps))
+
+
+def test_tester_generate_returns_scores_and_writes_midi(tmp_path):
+    """LatentRNNTester.generate (latent_rnn_tester.py:191-262): inpaint between two contexts, get the generated token
+    tensor and score objects back, export the lead as a Standard MIDI File (inpaintnet_b200/score.py)."""
+    from inpaintnet_b200.tester import LatentRNNTester
+    fx = torch.load(os.path.join(G, "latent_h32.pt"), weights_only=False)
+    m = build(fx, "fp32")
+    tester = LatentRNNTester(SyntheticFolkDataset(num_notes=fx["V"]), m)
+    past, future, target = fx["past"], fx["future"], fx["target"]
+    n_p, n_t, n_f = past.shape[1], target.shape[1], future.shape[1]
+    eps = [fx["eps_past"].transpose(0, 1).reshape(-1, fx["Z"]), fx["eps_future"].transpose(0, 1).reshape(-1, fx["Z"])]
+    with engine.inject_noise(eps=eps):
+        gen_score, gen_tensor, orig_score = tester.generate(past, future, target, n_t)
+    assert gen_tensor.shape == (past.shape[0], n_p + n_t + n_f, 24)
+    assert torch.equal(gen_tensor[:, :n_p].cpu(), past) and torch.equal(gen_tensor[:, n_p + n_t:].cpu(), future)
+    assert torch.equal(gen_tensor[:, n_p:n_p + n_t].cpu().reshape(past.shape[0], -1), fx["samples"][:, 0])   # the golden tokens
+    beats = (n_p + n_t + n_f) * 4
+    assert gen_score.quarter_length == beats == orig_score.quarter_length
+    path = gen_score.write("midi", fp=str(tmp_path / "inpainted.mid"))
+    data = open(path, "rb").read()
+    assert data[:4] == b"MThd" and data[14:18] == b"MTrk" and len(data) > 22
