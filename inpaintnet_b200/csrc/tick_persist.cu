@@ -66,8 +66,11 @@ struct TickPersist {
   unsigned long long* timing;
 };
 
-static inline int tk_smem_bytes(int H) {
-  return (H / 64) * GP_KB_BYTES + TK_WSTAGES * TK_WST_BYTES + GP_KB_BYTES + TK_NFLOAT * 4 + 4 * 128 * 8 + TK_NBAR * 8 + 16;
+static inline int tk_smem_bytes(int H, bool stream) {
+  const int nch = (H / 64) / TK_CS;
+  const int ring = stream ? (nch == 2 ? 3 : 5) * (GP_KB_BYTES + nch * TK_WST_BYTES)   // {A k-block + W tiles} stages
+                          : (H / 64) * GP_KB_BYTES + TK_WSTAGES * TK_WST_BYTES;        // resident A tile + W ring
+  return ring + GP_KB_BYTES + TK_NFLOAT * 4 + 4 * 128 * 8 + TK_NBAR * 8 + 16;
 }
 
 enum { PH_A = 0, PH_BH = 1, PH_BX = 2, PH_V = 3 };
@@ -88,12 +91,31 @@ __device__ __forceinline__ uint4 ldg_cg(const void* p) {   // L2 read (the data 
   return u;
 }
 
+// 256-bit loads (LDG.E.256 on sm_100): the gathers of the epilogue cost one LSU wavefront per lane and instruction (32
+// distinct 128-byte lines per warp), so halving the instruction count halves their time
+__device__ __forceinline__ void ldg_nc_32B(const void* p, uint4& a, uint4& b) {     // read-only data (folded table)
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg_cg_32B(const void* p, uint4& a, uint4& b) {     // written by a TMA store of this kernel
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
+}
+
 __device__ __forceinline__ void ld8f(const float* sp, float (&f)[8]) {   // 32-byte aligned shared-memory vector
   const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-template <bool SAVE>
+// STREAM (default): no resident A tile.  A ring stage holds one 64-wide k-block of the A operand AND the weight tile of
+// every chunk of this CTA for that k-block (16 + NCH x 24 KB; 3 stages at H = 512), filled by two producers that
+// arrive on the same stage barrier (weights run ahead, the A k-block waits for the exchange), consumed by 4 MMAs per
+// chunk.  That is 1.1 kcycles of MMA work per stage and 3.3 k in flight against the ring's ~2.8 kcycle round trip: the
+// three products of a tick stream at the SM's L2 -> shared-memory rate instead of the ring's round trip (DESIGN.md
+// section 4.3 (ii)).  The two chunk accumulators of a phase complete together and are drained one after the other
+// by all 16 epilogue warps.  STREAM = false is the first form of the kernel (resident A tile,
+// weights alone in a 3-stage ring, chunks one after the other), kept selectable (IPN_TICK_STREAM=0).
+template <bool SAVE, bool STREAM>
 __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(const __grid_constant__ TickPersist p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = p.H, KB = H >> 6, NT = p.nticks, TPB = p.tpb, B = p.B;
@@ -111,9 +133,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
     if (trace_on && t >= 8 && t < 10) p.timing[65536 / 2 + (role * 2 + (t - 8)) * 32 + ev] = (unsigned long long)clock64();
   };
 
+  const int SST_BYTES = GP_KB_BYTES + NCH * TK_WST_BYTES;   // STREAM: bytes of a ring stage
+  const int SSTAGES = NCH == 2 ? 3 : 5;
+  constexpr bool split = false;   // (a form with the epilogue warps split 8 + 8 over the chunks measured 5 % faster per tick but
+                                  //  needs 16-32 more live registers in an epilogue that already spills: not kept)
+  const int VKB = NCH == 2 ? 2 : 1;                          // k-blocks of the vocabulary projection per ring stage
   uint8_t* sA = smem;
-  uint8_t* sW = sA + KB * GP_KB_BYTES;
-  uint8_t* sStg = sW + TK_WSTAGES * TK_WST_BYTES;
+  uint8_t* sW = STREAM ? smem : sA + KB * GP_KB_BYTES;
+  uint8_t* sStg = STREAM ? smem + SSTAGES * SST_BYTES : sW + TK_WSTAGES * TK_WST_BYTES;
   float* sF = reinterpret_cast<float*>(sStg + GP_KB_BYTES);
   float* sBn0 = sF;             // [128] b_hn of layer 0, own units
   float* sHbr = sF + 128;       // 0.5 (b_ir + b_hr) layer 1
@@ -134,6 +161,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
   uint64_t* lg_empty = bars + 27;
   uint64_t* stg_ready = bars + 28;
   uint64_t* stg_free = bars + 29;
+  uint64_t* s_full = bars + 84;       // [6] STREAM ring: both producers arrived and their bytes landed
+  uint64_t* s_empty = bars + 90;      // [6]
   uint64_t* E0 = bars + 32;           // [2][8]: chunk kb of h0_t is in global memory (set = t & 1)
   uint64_t* E1 = bars + 48;           // [2][8]: h1_t
   uint64_t* EY = bars + 64;           // [2][8]: y0_t (only with a dropout mask)
@@ -147,11 +176,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
     if (lane == 0) {
       for (int s = 0; s < TK_WSTAGES; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
       for (int k = 0; k < 8; ++k) { ptx::mbar_init(&a_full[k], 1); ptx::mbar_init(&a_free[k], 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 16); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], split ? 8 : 16); }
       ptx::mbar_init(lg_full, 1);
       ptx::mbar_init(lg_empty, 16);
-      ptx::mbar_init(stg_ready, 16);
+      ptx::mbar_init(stg_ready, split ? 8 : 16);
       ptx::mbar_init(stg_free, 1);
+      for (int k = 0; k < 6; ++k) { ptx::mbar_init(&s_full[k], 2); ptx::mbar_init(&s_empty[k], 1); }
       for (int k = 0; k < 16; ++k) { ptx::mbar_init(&E0[k], 1); ptx::mbar_init(&E1[k], 1); ptx::mbar_init(&EY[k], 1); }
       ptx::fence_barrier_init();
     }
@@ -208,6 +238,36 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         int stage = 0;
         uint32_t phase = 0;
         int kind, t;
+        if constexpr (STREAM) {
+          for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
+            if (t >= NT) continue;
+            const int kstep = (kind == PH_V) ? VKB : 1;   // V: VKB k-blocks per stage [A x VKB | W_v x VKB]
+            for (int kb = 0; kb < KB; kb += kstep) {
+              ptx::mbar_wait(&s_empty[stage], phase ^ 1);
+              uint8_t* dst = smem + stage * SST_BYTES + GP_KB_BYTES;
+              if ((p.dbg & 1) && t > 0) {
+                ptx::mbar_arrive(&s_full[stage]);
+              } else if (kind == PH_V) {
+                ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(VKB * 64 * 128));
+                for (int x = 0; x < VKB; ++x)
+                  ptx::tma_load_2d(smem + stage * SST_BYTES + VKB * GP_KB_BYTES + x * 64 * 128, &p.tmWv, &s_full[stage], (kb + x) * 64, 0);
+              } else {
+                ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(NCH * TK_WST_BYTES));
+                for (int ci = 0; ci < NCH; ++ci) {
+                  const int c = c_lo + ci;
+                  uint8_t* d = dst + ci * TK_WST_BYTES;
+                  if (kind == PH_A) ptx::tma_load_3d(d, &p.tmW0, &s_full[stage], kb * 64, c * 64, 0);
+                  else if (kind == PH_BH) ptx::tma_load_3d(d, &p.tmW1, &s_full[stage], kb * 64, c * 64, 0);
+                  else {   // rows [n | r | z]
+                    ptx::tma_load_3d(d, &p.tmWxn, &s_full[stage], kb * 64, c * 64, 2);
+                    ptx::tma_load_3d(d + 64 * 128, &p.tmWxrz, &s_full[stage], kb * 64, c * 64, 0);
+                  }
+                }
+              }
+              if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else
         for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
           if (t >= NT) continue;
           const int nch = kind == PH_V ? 1 : NCH;
@@ -252,6 +312,74 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
       const uint64_t descA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024);
       const uint64_t descW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024);
       int kind, t;
+      if constexpr (STREAM) {
+        for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
+          if (t >= NT) continue;
+          const int nch = kind == PH_V ? 1 : NCH;
+          const int ttr = kind == PH_BX || kind == PH_V ? t : t - 1;
+          if (kind == PH_A || kind == PH_BH) {
+            for (int b = 0; b < nch; ++b) {
+              wait_acc(&tmem_empty[b], (uint32_t)((n_write[b] & 1) ^ 1), tm, w_te);
+              ++n_write[b];
+            }
+            if (kind == PH_BH && t > 0) wait_acc(lg_empty, (uint32_t)((t - 1) & 1), tm, w_lg);
+          } else if (kind == PH_V && t == NT - 1) {
+            wait_acc(&tmem_empty[0], (uint32_t)((n_write[0] & 1) ^ 1), tm, w_te);   // last tick: no A(t+1) has waited for it
+          }
+          ptx::tc_fence_after();
+          if (lane == 0) tr(0, ttr, kind * 4);
+          const int kstep = (kind == PH_V) ? VKB : 1;
+          for (int kb = 0; kb < KB; kb += kstep) {
+            wait_acc(&s_full[stage], phase, tm, w_wf);
+            ptx::tc_fence_after();
+            if (lane == 0 && kb == 0) tr(0, ttr, kind * 4 + 1);
+            const uint64_t da0 = descA0 + (uint64_t)((stage * SST_BYTES) >> 4);
+            if (ptx::elect_one()) {
+              if (kind == PH_V) {
+                for (int x = 0; x < VKB; ++x) {
+                  const uint64_t dax = da0 + (uint64_t)((x * GP_KB_BYTES) >> 4);
+                  const uint64_t dwx = da0 + (uint64_t)((VKB * GP_KB_BYTES + x * 64 * 128) >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    if (p.dbg & 2) break;
+                    ptx::umma_bf16(tmem_base + 192, dax + (uint64_t)(kk * 2), dwx + (uint64_t)(kk * 2), id64, (kb + x > 0 || kk > 0) ? 1u : 0u);
+                  }
+                }
+              } else
+              for (int ci = 0; ci < nch; ++ci) {
+                const uint64_t dw0 = da0 + (uint64_t)((GP_KB_BYTES + ci * TK_WST_BYTES) >> 4);
+                const uint32_t dbase = tmem_base + (uint32_t)(ci * 256);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (p.dbg & 2) break;
+                  const uint64_t da = da0 + (uint64_t)(kk * 2), dw = dw0 + (uint64_t)(kk * 2);
+                  const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+                  if (kind == PH_A) ptx::umma_bf16(dbase, da, dw, id192, acc);
+                  else if (kind == PH_BH) ptx::umma_bf16(dbase + 64, da, dw, id192, acc);
+                  else if (kind == PH_V) ptx::umma_bf16(tmem_base + 192, da, dw, id64, acc);
+                  else if (acc) ptx::umma_bf16(dbase, da, dw, id192, 1u);
+                  else {   // first Bx MMA of the chunk: n_x starts fresh, r and z continue on top of Bh
+                    ptx::umma_bf16(dbase, da, dw, id64, 0u);
+                    ptx::umma_bf16(dbase + 64, da, dw + (uint64_t)((64 * 128) >> 4), id128, 1u);
+                  }
+                }
+              }
+              ptx::umma_commit(&s_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+          }
+          if (ptx::elect_one()) {
+            if (kind == PH_A || kind == PH_BX) {
+              for (int b = 0; b < nch; ++b) ptx::umma_commit(&tmem_full[b]);
+            } else if (kind == PH_V) {
+              ptx::umma_commit(lg_full);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tr(0, ttr, kind * 4 + 2);
+        }
+      } else
       for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
         if (t >= NT) continue;
         const unsigned key = a_key(kind, t);
@@ -377,10 +505,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         const bool tm = p.timing != nullptr && (p.dbg & 16);
         long long w_fr = 0, w_ex = 0;
         int kind, t;
+        int stage = 0;
+        uint32_t phase = 0;
         for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
           if (t >= NT) continue;
           const unsigned key = a_key(kind, t);
-          if (key == prev_key) continue;
+          if (!STREAM && key == prev_key) continue;   // STREAM: the k-blocks of every phase pass through the ring
           prev_key = key;
           const int j = t % TPB;
           // which exchange the source waits for: (barrier array, tick); none for the initial state of a beat
@@ -393,8 +523,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           const CUtensorMap* tmap = (key >> 28) == 0 ? &p.tmH0 : (key >> 28) == 1 ? &p.tmH1 : &p.tmY0;
           const int coord = (int)(key & 0x0fffffffu);
           const int ttr = kind == PH_BX || kind == PH_V ? t : t - 1;
+          const int kstep = (STREAM && kind == PH_V) ? VKB : 1;
           for (int kb = 0; kb < KB; ++kb) {
-            if (n_load > 0) wait_acc(&a_free[kb], (uint32_t)((n_load - 1) & 1), tm, w_fr);
+            if (STREAM) { if (kb % kstep == 0) wait_acc(&s_empty[stage], phase ^ 1, tm, w_fr); }
+            else if (n_load > 0) wait_acc(&a_free[kb], (uint32_t)((n_load - 1) & 1), tm, w_fr);
             if (kb == 0) tr(3, ttr, kind * 4);
             if (e != nullptr) {
               uint64_t* hs = e + (te & 1) * 8 + kb;
@@ -405,8 +537,15 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
               if (tm) w_ex += clock64() - t0;
               ptx::fence_proxy_async_all();
             }
-            ptx::mbar_arrive_expect_tx(&a_full[kb], GP_KB_BYTES);
-            ptx::tma_load_2d(sA + kb * GP_KB_BYTES, tmap, &a_full[kb], kb * 64, coord);
+            if (STREAM) {
+              // one arrival per stage (the barrier counts two: this thread and the weight producer), all bytes announced with it
+              if (kb % kstep == 0) ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(kstep * GP_KB_BYTES));
+              ptx::tma_load_2d(smem + stage * SST_BYTES + (kb % kstep) * GP_KB_BYTES, tmap, &s_full[stage], kb * 64, coord);
+              if (kb % kstep == kstep - 1 && ++stage == SSTAGES) { stage = 0; phase ^= 1; }
+            } else {
+              ptx::mbar_arrive_expect_tx(&a_full[kb], GP_KB_BYTES);
+              ptx::tma_load_2d(sA + kb * GP_KB_BYTES, tmap, &a_full[kb], kb * 64, coord);
+            }
             if (kb == 0) tr(3, ttr, kind * 4 + 1);
           }
           tr(3, ttr, kind * 4 + 2);
@@ -452,8 +591,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
       const int i = t / TPB, j = t - i * TPB;
       if (j > 0) wait_acc(e + ((t - 1) & 1) * 8 + c, (uint32_t)(((t - 1) >> 1) & 1), tm, w_hp);
       const __nv_bfloat16* src = hseq + ((long long)j * B4 + (long long)i * B + rbase + row) * H + c * 64 + sub * 16;
-      hp[0] = ldg_cg(src);
-      hp[1] = ldg_cg(src + 8);
+      if (p.dbg & 128) { hp[0] = make_uint4(0, 0, 0, 0); hp[1] = hp[0]; return; }
+      ldg_cg_32B(src, hp[0], hp[1]);
     };
 
     auto l0_epilogue = [&](int t) {
@@ -468,12 +607,17 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           const uint4* tb = p.ftab + (long long)tokv * (3 * vpr) + c * 8 + sub * 2;
           const uint4* pb = p.BPblk + (rtb * 3 * vpr + c * 8 + sub * 2) * 128 + row;
 #pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            if (p.dbg & 64) { pv[g][0] = make_uint4(0, 0, 0, 0); pv[g][1] = pv[g][0]; continue; }
+            ldg_nc_32B(tb + g * vpr, pv[g][0], pv[g][1]);   // 32 contiguous bytes per gate
+          }
+#pragma unroll
           for (int g = 0; g < 3; ++g)
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               float a[8], bb[8];
-              unpack8(__ldg(tb + g * vpr + v), a);
-              unpack8(ldg_stream(pb + (g * vpr + v) * 128), bb);
+              unpack8(pv[g][v], a);
+              unpack8((p.dbg & 32) ? make_uint4(0, 0, 0, 0) : ldg_stream(pb + (g * vpr + v) * 128), bb);
 #pragma unroll
               for (int k = 0; k < 8; ++k) a[k] += bb[k];
               pv[g][v] = pack8(a);
@@ -484,8 +628,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         uint2 mk[2] = {make_uint2(0x01010101u, 0x01010101u), make_uint2(0x01010101u, 0x01010101u)};
         if (masked) {
           const unsigned char* mp = p.mask + (R0 + row) * H + c * 64 + sub * 16;
-          mk[0] = *reinterpret_cast<const uint2*>(mp);
-          mk[1] = *reinterpret_cast<const uint2*>(mp + 8);
+          const uint4 m16 = *reinterpret_cast<const uint4*>(mp);   // 16 keep bytes = this thread's 16 units
+          mk[0] = make_uint2(m16.x, m16.y);
+          mk[1] = make_uint2(m16.z, m16.w);
         }
         wait_acc(&tmem_full[b], (uint32_t)(n_full[b] & 1), tm, w_tf);
         ++n_full[b];
@@ -705,8 +850,9 @@ bool tick_persist_shape_ok(const IpnTickDecode* p) {
   if (A.reverse || Bd.reverse || Bd.pvec != nullptr || Bd.table != nullptr) return false;
   if ((A.gates != nullptr) != (Bd.gates != nullptr)) return false;
   if (A.gates != nullptr && (!p->gates_blocked || !al16(A.gates) || !al16(Bd.gates))) return false;
-  if (p->mask != nullptr && reinterpret_cast<uintptr_t>(p->mask) % 8 != 0) return false;
-  if (!al16(p->yt0) || !al16(p->yt1) || !al16(A.hseq) || !al16(Bd.hseq) || !al16(p->w_ih1) || !al16(p->w_v)) return false;
+  if (p->mask != nullptr && reinterpret_cast<uintptr_t>(p->mask) % 16 != 0) return false;
+  if (!al16(p->yt0) || !al16(p->yt1) || !al16(p->w_ih1) || !al16(p->w_v)) return false;
+  if (reinterpret_cast<uintptr_t>(A.hseq) % 32 != 0 || reinterpret_cast<uintptr_t>(Bd.hseq) % 32 != 0) return false;   // 256-bit h_prev loads
   if (A.tok != p->tokprev) return false;
   if (7LL * 4 * p->B >= (1LL << 28)) return false;
   return true;
@@ -715,7 +861,8 @@ bool tick_persist_shape_ok(const IpnTickDecode* p) {
 int tick_persist_decode(const IpnTickDecode* p, void* ws, long long ws_bytes, cudaStream_t stream) {
   const int B = p->B, H = p->H, V = p->V;
   const long long B4 = 4LL * B;
-  IPN_REQUIRE(ws != nullptr && al16(ws) && ws_bytes >= 128LL * 3 * H * 2, IPN_ERR_ARG, "tick_persist_decode: workspace too small");
+  IPN_REQUIRE(ws != nullptr && reinterpret_cast<uintptr_t>(ws) % 32 == 0 && ws_bytes >= 128LL * 3 * H * 2, IPN_ERR_ARG,
+              "tick_persist_decode: workspace too small or not 32-byte aligned");
   TickPersist q;
   memset(&q, 0, sizeof(q));
   q.B = B; q.H = H; q.V = V; q.nticks = 24; q.tpb = 6;
@@ -753,10 +900,12 @@ int tick_persist_decode(const IpnTickDecode* p, void* ws, long long ws_bytes, cu
   q.dbg = getenv("IPN_TICK_DBG") ? atoi(getenv("IPN_TICK_DBG")) : 0;
   const bool save = p->l0.gates != nullptr;
   const int ntw = B / GP_ROWS;
-  const int smem = tk_smem_bytes(H);
+  const bool stream_form = getenv("IPN_TICK_STREAM") ? atoi(getenv("IPN_TICK_STREAM")) != 0 : true;
+  const int smem = tk_smem_bytes(H, stream_form);
   auto launch = [&](auto kern, bool* configured) -> int {
     if (!*configured) {
-      IPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tk_smem_bytes(512)));
+      const int a = tk_smem_bytes(512, stream_form), b = tk_smem_bytes(256, stream_form);
+      IPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a > b ? a : b));
       *configured = true;
     }
     // algorithmic work: three H x 3H products and the vocabulary projection per row and tick;
@@ -781,9 +930,14 @@ int tick_persist_decode(const IpnTickDecode* p, void* ws, long long ws_bytes, cu
     IPN_LAUNCH_CHECK();
     return IPN_OK;
   };
-  static bool cfgd[2] = {false, false};
-  if (save) IPN_PROPAGATE(launch(tick_decode_persist_kernel<true>, &cfgd[0]));
-  else IPN_PROPAGATE(launch(tick_decode_persist_kernel<false>, &cfgd[1]));
+  static bool cfgd[4] = {false, false, false, false};
+  if (stream_form) {
+    if (save) IPN_PROPAGATE(launch(tick_decode_persist_kernel<true, true>, &cfgd[0]));
+    else IPN_PROPAGATE(launch(tick_decode_persist_kernel<false, true>, &cfgd[1]));
+  } else {
+    if (save) IPN_PROPAGATE(launch(tick_decode_persist_kernel<true, false>, &cfgd[2]));
+    else IPN_PROPAGATE(launch(tick_decode_persist_kernel<false, false>, &cfgd[3]));
+  }
   return IPN_OK;
 }
 

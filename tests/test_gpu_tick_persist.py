@@ -24,9 +24,11 @@ DEV = "cuda"
 Z = 256
 
 
-def _decode(sd, V, H, B, train, persist, seed=29):
+def _decode(sd, V, H, B, train, persist, seed=29, stream=True):
     old = os.environ.get("IPN_TICK_PERSIST")
+    old_s = os.environ.get("IPN_TICK_STREAM")
     os.environ["IPN_TICK_PERSIST"] = "1" if persist else "0"
+    os.environ["IPN_TICK_STREAM"] = "1" if stream else "0"     # both read per call by the library
     try:
         m = MeasureVAE(SyntheticFolkDataset(num_notes=V), encoder_hidden_size=H, decoder_hidden_size=H, latent_space_dim=Z)
         m.load_state_dict(sd)
@@ -47,10 +49,11 @@ def _decode(sd, V, H, B, train, persist, seed=29):
         torch.cuda.synchronize()
         launches = ops.lib().ipn_launch_count() - n0
     finally:
-        if old is None:
-            os.environ.pop("IPN_TICK_PERSIST", None)
-        else:
-            os.environ["IPN_TICK_PERSIST"] = old
+        for k, v in (("IPN_TICK_PERSIST", old), ("IPN_TICK_STREAM", old_s)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return dict(w=w.cpu(), s=s.cpu(), tokens=tokens, eps=eps, enc=enc, beat=beat, tick=tick, launches=launches)
 
 
@@ -75,6 +78,10 @@ def test_persistent_tick_decode_matches_per_tick_path_and_oracle(V, H, train):
     sd = recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), 4321)
     a = _decode(sd, V, H, B, train, persist=True)
     b = _decode(sd, V, H, B, train, persist=False)
+    # the first form of the kernel (resident A tile, weights alone in the ring: IPN_TICK_STREAM=0) issues the same MMAs in
+    # the same order on the same operands: bit-identical outputs
+    a0 = _decode(sd, V, H, B, train, persist=True, stream=False)
+    assert torch.equal(a0["s"], a["s"]) and torch.equal(a0["w"], a["w"])
     # one launch (+ the table fold) instead of 24 x 5
     assert a["launches"] + 100 < b["launches"], (a["launches"], b["launches"])
     same = (a["s"] == b["s"]).all(2).all(1)
