@@ -91,17 +91,8 @@ __device__ __forceinline__ uint4 ldg_cg(const void* p) {   // L2 read (the data 
   return u;
 }
 
-// 256-bit loads (LDG.E.256 on sm_100): the gathers of the epilogue cost one LSU wavefront per lane and instruction (32
-// distinct 128-byte lines per warp), so halving the instruction count halves their time
-__device__ __forceinline__ void ldg_nc_32B(const void* p, uint4& a, uint4& b) {     // read-only data (folded table)
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-}
-__device__ __forceinline__ void ldg_cg_32B(const void* p, uint4& a, uint4& b) {     // written by a TMA store of this kernel
-  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
-}
-
+// (256-bit gathers: ldg_nc_32B / ldg_cg_32B in gru_persist.cuh -- a gather costs one LSU wavefront per lane and
+// instruction, 32 distinct 128-byte lines per warp, so halving the instruction count halves its time)
 __device__ __forceinline__ void ld8f(const float* sp, float (&f)[8]) {   // 32-byte aligned shared-memory vector
   const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
