@@ -9,7 +9,7 @@
 // Every operation is row-local, so a 128-row tile never talks to another tile.  A cluster of 4 CTAs owns one tile
 // (32 tiles -> 128 SMs at 4096 measures); CTA `rank` owns hidden units [rank*H/4, (rank+1)*H/4) of BOTH layers.
 // W_hh0, W_ih1, W_hh1 and W_v stream from L2 through one TMA ring (the weights of a tick are 4.7 MB, far beyond
-// shared memory); ONE 128-row x H activation tile (the A operand) is refilled per phase:
+// shared memory) together with the 128-row x H activation tile that is the A operand of the phase:
 //
 //   phase   A operand   B operand          accumulators (TMEM columns, per 64-unit chunk b of this CTA)
 //   A(t)    h0_{t-1}    W_hh0 [r z n]      b*256 + [0,192)
@@ -18,12 +18,10 @@
 //   V(t)    h1_t        W_v                [192,256)          (64 logits; every CTA of the cluster computes them)
 //
 // issued in the order  A(0) Bh(0) | Bx(t) A(t+1) V(t) Bh(t+1) | ...  so that the tensor pipe runs A(t+1) while the
-// layer-1 epilogue of tick t and the exchange of h1_t are in flight, and Bh(t+1) while layer 0's are.  A(t+1) and
-// Bx(t) share their operand when there is no dropout mask, V(t) and Bh(t+1) always do within a beat: 2-3 refills
-// of the tile per tick.  h slices travel between the 4 CTAs as in the column split of the layer kernel
-// (gru_persist.cu): TMA store to the time-major history (which the backward pass needs anyway), remote mbarrier
-// arrive with release semantics, TMA reload from L2.  The token never leaves the SM: each epilogue thread keeps the
-// argmax of its row in a register for the next tick's table gather.
+// layer-1 epilogue of tick t and the exchange of h1_t are in flight.  h slices travel between the 4 CTAs as in the
+// column split of the layer kernel (gru_persist.cu): TMA store to the time-major history (which the backward pass
+// needs anyway), one cluster fence + relaxed remote mbarrier arrives, TMA reload from L2.  The token never leaves the
+// SM: each epilogue thread keeps the argmax of its row in a register for the next tick's table gather.
 #include "gru_persist.cuh"
 #include <stdlib.h>
 
@@ -126,8 +124,6 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
 
   const int SST_BYTES = GP_KB_BYTES + NCH * TK_WST_BYTES;   // STREAM: bytes of a ring stage
   const int SSTAGES = NCH == 2 ? 3 : 5;
-  constexpr bool split = false;   // (a form with the epilogue warps split 8 + 8 over the chunks measured 5 % faster per tick but
-                                  //  needs 16-32 more live registers in an epilogue that already spills: not kept)
   const int VKB = NCH == 2 ? 2 : 1;                          // k-blocks of the vocabulary projection per ring stage
   uint8_t* sA = smem;
   uint8_t* sW = STREAM ? smem : sA + KB * GP_KB_BYTES;
@@ -167,10 +163,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
     if (lane == 0) {
       for (int s = 0; s < TK_WSTAGES; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
       for (int k = 0; k < 8; ++k) { ptx::mbar_init(&a_full[k], 1); ptx::mbar_init(&a_free[k], 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], split ? 8 : 16); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 16); }
       ptx::mbar_init(lg_full, 1);
       ptx::mbar_init(lg_empty, 16);
-      ptx::mbar_init(stg_ready, split ? 8 : 16);
+      ptx::mbar_init(stg_ready, 16);
       ptx::mbar_init(stg_free, 1);
       for (int k = 0; k < 6; ++k) { ptx::mbar_init(&s_full[k], 2); ptx::mbar_init(&s_empty[k], 1); }
       for (int k = 0; k < 16; ++k) { ptx::mbar_init(&E0[k], 1); ptx::mbar_init(&E1[k], 1); ptx::mbar_init(&EY[k], 1); }
