@@ -16,11 +16,13 @@ P = torch.randn(ndir, T * B, 3 * H, device=DEV).bfloat16()
 hseq = torch.zeros(ndir, (T + 1) * B, H, dtype=torch.bfloat16, device=DEV)
 gates = torch.zeros(ndir, T * B, ops.gates_cols(H), dtype=torch.bfloat16, device=DEV)
 y = torch.zeros(T * B, ndir * H, dtype=torch.bfloat16, device=DEV)
-dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), gates=gates[d].data_ptr(),
+NOSAVE = os.environ.get("NOSAVE", "0") != "0"      # inference: no saved gates
+dirs = [ops.gru_dir(whh[d].data_ptr(), bhh[d].data_ptr(), hseq[d].data_ptr(), gates=0 if NOSAVE else gates[d].data_ptr(),
                     P=P[d].data_ptr(), ldP=3 * H, reverse=d, y_col0=d * H) for d in range(ndir)]
 ncta = (B // 128) * ndir
 timing = torch.zeros(ncta * 16, dtype=torch.int64, device=DEV)
-ops.lib().ipn_dbg_set_timing_buffer(timing.data_ptr())
+if os.environ.get("NOTIMING", "0") == "0":   # the wait counters cost ~150 cycles per clock64 read: off for clean launch times
+    ops.lib().ipn_dbg_set_timing_buffer(timing.data_ptr())
 ops.prof_enable(True)
 for _ in range(4):
     ops.gru_layer_fwd(prec, T, B, H, dirs, y=y.data_ptr(), ld_y=ndir * H)
