@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
   const uint16_t pair_mask = (uint16_t)(3u << lead_rank);
   const int c_lo = CS > 1 ? (int)colrank * (KB / CS) : 0, c_hi = c_lo + KB / CS;   // chunks (64 hidden units) of this CTA
 
+  const bool trace_on = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto tr = [&](int role, int t, int ev) {
+    if (trace_on && t >= 8 && t < 10 && ev < 32) p.trace[(role * 2 + (t - 8)) * 32 + ev] = (unsigned long long)clock64();
+  };
   uint8_t* sA = smem;
   uint8_t* sW = sA + KB * GP_KB_BYTES;
   uint8_t* sStg = sW + GPF_W_RING;
@@ -261,11 +265,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           const int b = i & 1, n = i >> 1;
           wait_acc(&tmem_empty[b], (n & 1) ^ 1, tm, w_te);
           ptx::tc_fence_after();
+          if (lane == 0) tr(0, t, (c - c_lo) * 3);
           const uint32_t dcol = tmem_base + (uint32_t)(b * 256);
           for (int kb = 0; kb < KB; ++kb) {
             if (c == c_lo) wait_acc(&a_full[kb], t & 1, tm, w_af);
             wait_acc(&w_full[stage], phase, tm, w_wf);
             ptx::tc_fence_after();
+            if (lane == 0 && kb == KB - 1) tr(0, t, (c - c_lo) * 3 + 1);
             const uint64_t da0 = descA0 + (uint64_t)((kb * GP_KB_BYTES) >> 4);
             const uint64_t dw0 = descW0 + (uint64_t)((stage * WST_BYTES) >> 4);
             if (ptx::elect_one()) {
@@ -290,6 +296,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
             else ptx::umma_commit(&tmem_full[b]);
           }
           __syncwarp();
+          if (lane == 0) tr(0, t, (c - c_lo) * 3 + 2);
         }
       if (tm && lane == 0) {
         unsigned long long* o = p.timing + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
         const int out_slot = D.reverse ? tt : tt + 1;
         for (int c = c_lo; c < c_hi; ++c, ++i) {
           wait_acc(stg_ready, i & 1, tm, w_sr);
+          tr(2, t, (c - c_lo) * 3);
           const long long ts0 = tm ? clock64() : 0;
           ptx::tma_store_2d(&D.tmH, sStg, c * 64, out_slot * Bt + rbase);
           if (D.has_y) ptx::tma_store_2d(&D.tmY, sStg, D.y_col0 + c * 64, tt * Bt + rbase);
@@ -314,6 +322,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           ptx::bulk_wait_read0();
           ptx::mbar_arrive(stg_free);
           ptx::bulk_wait0();
+          tr(2, t, (c - c_lo) * 3 + 1);
           if (CS > 1) {   // the peer reloads this chunk of h_t from L2 as a k-block of its next step's A operand
             uint64_t* hs = (t & 1) ? &h_stored_odd[c] : &h_stored[c];
             ptx::mbar_arrive(hs);
@@ -327,6 +336,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           } else {
             ptx::mbar_arrive(&h_stored[c]);
           }
+          tr(2, t, (c - c_lo) * 3 + 2);
           if (tm) w_st += clock64() - ts0;
         }
       }
@@ -348,13 +358,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
             wait_acc(&a_free[kb], (t - 1) & 1, tm, w_fr);
             if (CS > 1) {   // step t-1's stores: barrier set (t-1) & 1, phase ((t-1) >> 1) & 1; peer chunks at cluster scope
               uint64_t* hs = ((t - 1) & 1) ? &h_stored_odd[kb] : &h_stored[kb];
-              if (kb < c_lo || kb >= c_hi) ptx::mbar_wait_cluster(hs, ((t - 1) >> 1) & 1);
+              if ((kb < c_lo || kb >= c_hi) && !(p.dbg & 64)) ptx::mbar_wait_cluster(hs, ((t - 1) >> 1) & 1);
               else wait_acc(hs, ((t - 1) >> 1) & 1, tm, w_hs);
             } else {
               wait_acc(&h_stored[kb], (t - 1) & 1, tm, w_hs);
             }
-            ptx::fence_proxy_async_all();
+            if (!(p.dbg & 32)) ptx::fence_proxy_async_all();
           }
+          tr(3, t, kb);
           if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], PAIR ? 2 * GP_KB_BYTES : GP_KB_BYTES);
           if (PAIR) ptx::tma_load_2d_pair(sA + kb * GP_KB_BYTES, &D.tmH, &a_full[kb], kb * 64, in_slot * Bt + rbase);
           else ptx::tma_load_2d(sA + kb * GP_KB_BYTES, &D.tmH, &a_full[kb], kb * 64, in_slot * Bt + rbase);
@@ -431,8 +442,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       uint4 pv[3][2];
       load_p(pv, t, c);  // L2 hits (bulk-prefetched by the producer warp); latency hidden by the other 3 warps of the SMSP
       if (leader) ptx::mbar_wait(&a_full[c], t & 1);  // h_{t-1} k-block c visible to this thread (read below)
+      if (threadIdx.x == 128) tr(1, t, (c - c_lo) * 4);
       wait_acc(&tmem_full[b], n & 1, tm, w_tf);
       ptx::tc_fence_after();
+      if (threadIdx.x == 128) tr(1, t, (c - c_lo) * 4 + 1);
       if (!(p.dbg & 4)) {
         const uint32_t abase = sA_u + c * GP_KB_BYTES + row * 128;
         // accumulator column of (gate g, unit u of the chunk): pair: (u / 32) * 96 + g * 32 + u % 32 ; single: g * 64 + u
@@ -477,6 +490,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       } else {
         wait_acc(stg_free, (i & 1) ^ 1, tm, w_sf);
       }
+      if (threadIdx.x == 128) tr(1, t, (c - c_lo) * 4 + 2);
       ptx::tc_fence_before();
       ptx::fence_proxy_async();  // staging-tile writes -> visible to the TMA store
       __syncwarp();
@@ -590,6 +604,7 @@ int gru_persist_fwd(const IpnGruLayer* L, void* ws, long long ws_bytes, cudaStre
   // flight) / (commit -> refill -> landed round trip), not L2 bandwidth.  IPN_GPF_PAIRCS=0 keeps the plain column split.
   static const int paircs_on = getenv("IPN_GPF_PAIRCS") ? atoi(getenv("IPN_GPF_PAIRCS")) : 1;
   const bool pair = pair_on && ntw % 2 == 0 && (cs == 1 || (cs == 2 && paircs_on && 2 * ntw * L->ndir <= 132));
+  p.trace = g_dbg_timing != nullptr ? g_dbg_timing + 32768 : nullptr;   // the diagnostics buffer holds 65536 entries then
   if (cs > 1) p.timing = nullptr;
   char* wsp = reinterpret_cast<char*>(ws);
   bool save = false;

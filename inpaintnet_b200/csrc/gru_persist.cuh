@@ -47,6 +47,7 @@ struct GruPersistFwd {
   int row0, s_begin, s_end;   // window of this call: rows [row0, row0 + 128*gridDim.x), processing steps [s_begin, s_end)
   int dbg;                    // diagnostics (IPN_GPF_DBG): 1 no P loads, 2 no gate stores, 4 no gate math, 8 no W loads
   unsigned long long* timing; // per-CTA wait-cycle counters (ipn_dbg_set_timing_buffer), normally null
+  unsigned long long* trace;  // cycle stamps of CTA (0,0), steps 8 and 9: [role][step - 8][event] x 32 (tests/dev/persist_time.py)
 };
 
 struct GruPersistBwdDir {

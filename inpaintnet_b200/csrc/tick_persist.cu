@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
   const int SST_BYTES = GP_KB_BYTES + NCH * TK_WST_BYTES;   // STREAM: bytes of a ring stage
   const int SSTAGES = NCH == 2 ? 3 : 5;
   const int VKB = NCH == 2 ? 2 : 1;                          // k-blocks of the vocabulary projection per ring stage
+  // STREAM: k-blocks are consumed in PRODUCTION order -- every CTA of the cluster stores its first chunk, then its second,
+  // so chunks {0,2,4,6} of a new h arrive before {1,3,5,7}: i-th k-block of a phase = chunk kperm(i)
+  const int KPB = KB / NCH;                                  // k-blocks per arrival batch
+  auto kperm = [&](int i) { return (i % KPB) * NCH + i / KPB; };
   uint8_t* sA = smem;
   uint8_t* sW = STREAM ? smem : sA + KB * GP_KB_BYTES;
   uint8_t* sStg = STREAM ? smem + SSTAGES * SST_BYTES : sW + TK_WSTAGES * TK_WST_BYTES;
@@ -229,7 +233,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
             if (t >= NT) continue;
             const int kstep = (kind == PH_V) ? VKB : 1;   // V: VKB k-blocks per stage [A x VKB | W_v x VKB]
-            for (int kb = 0; kb < KB; kb += kstep) {
+            for (int i = 0; i < KB; i += kstep) {
+              const int kb = kperm(i);
               ptx::mbar_wait(&s_empty[stage], phase ^ 1);
               uint8_t* dst = smem + stage * SST_BYTES + GP_KB_BYTES;
               if ((p.dbg & 1) && t > 0) {
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
               } else if (kind == PH_V) {
                 ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(VKB * 64 * 128));
                 for (int x = 0; x < VKB; ++x)
-                  ptx::tma_load_2d(smem + stage * SST_BYTES + VKB * GP_KB_BYTES + x * 64 * 128, &p.tmWv, &s_full[stage], (kb + x) * 64, 0);
+                  ptx::tma_load_2d(smem + stage * SST_BYTES + VKB * GP_KB_BYTES + x * 64 * 128, &p.tmWv, &s_full[stage], kperm(i + x) * 64, 0);
               } else {
                 ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(NCH * TK_WST_BYTES));
                 for (int ci = 0; ci < NCH; ++ci) {
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           ptx::tc_fence_after();
           if (lane == 0) tr(0, ttr, kind * 4);
           const int kstep = (kind == PH_V) ? VKB : 1;
-          for (int kb = 0; kb < KB; kb += kstep) {
+          for (int kb = 0; kb < KB; kb += kstep) {   // kb: position in the phase's k-block sequence (chunk kperm(kb))
             wait_acc(&s_full[stage], phase, tm, w_wf);
             ptx::tc_fence_after();
             if (lane == 0 && kb == 0) tr(0, ttr, kind * 4 + 1);
@@ -494,6 +499,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
         int kind, t;
         int stage = 0;
         uint32_t phase = 0;
+        int acquired[3] = {-1, -1, -1};   // last tick whose E0 / E1 / EY exchange this thread has acquired (all chunks)
         for (int step = 0; tk_phase(step, NT, kind, t); ++step) {
           if (t >= NT) continue;
           const unsigned key = a_key(kind, t);
@@ -511,9 +517,37 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
           const int coord = (int)(key & 0x0fffffffu);
           const int ttr = kind == PH_BX || kind == PH_V ? t : t - 1;
           const int kstep = (STREAM && kind == PH_V) ? VKB : 1;
+          if constexpr (STREAM) {
+            // one acquire + proxy fence per ARRIVAL BATCH (first chunks of the 4 CTAs, then their second chunks) instead
+            // of per k-block (each cost ~1.3 kcycles of this thread), and none when an earlier phase already acquired
+            // this exchange (A(t+1) after Bx(t) without a mask, Bh(t+1) after V(t))
+            const int which = e == E0 ? 0 : e == E1 ? 1 : 2;
+            const bool need = e != nullptr && acquired[which] != te;
+            for (int i = 0; i < KB; ++i) {
+              const int kb = kperm(i);
+              if (i % kstep == 0) wait_acc(&s_empty[stage], phase ^ 1, tm, w_fr);
+              if (i == 0) tr(3, ttr, kind * 4);
+              if (need && i % KPB == 0) {
+                const uint32_t par = (uint32_t)((te >> 1) & 1);
+                const long long t0 = tm ? clock64() : 0;
+                for (int x = 0; x < KPB; ++x) {
+                  const int kx = kperm(i + x);
+                  uint64_t* hs = e + (te & 1) * 8 + kx;
+                  if (kx < c_lo || kx >= c_hi) ptx::mbar_wait_cluster(hs, par);
+                  else ptx::mbar_wait(hs, par);
+                }
+                if (tm) w_ex += clock64() - t0;
+                ptx::fence_proxy_async_all();
+              }
+              if (i % kstep == 0) ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(kstep * GP_KB_BYTES));
+              ptx::tma_load_2d(smem + stage * SST_BYTES + (i % kstep) * GP_KB_BYTES, tmap, &s_full[stage], kb * 64, coord);
+              if (i % kstep == kstep - 1 && ++stage == SSTAGES) { stage = 0; phase ^= 1; }
+              if (i == 0) tr(3, ttr, kind * 4 + 1);
+            }
+            if (need) acquired[which] = te;
+          } else
           for (int kb = 0; kb < KB; ++kb) {
-            if (STREAM) { if (kb % kstep == 0) wait_acc(&s_empty[stage], phase ^ 1, tm, w_fr); }
-            else if (n_load > 0) wait_acc(&a_free[kb], (uint32_t)((n_load - 1) & 1), tm, w_fr);
+            if (n_load > 0) wait_acc(&a_free[kb], (uint32_t)((n_load - 1) & 1), tm, w_fr);
             if (kb == 0) tr(3, ttr, kind * 4);
             if (e != nullptr) {
               uint64_t* hs = e + (te & 1) * 8 + kb;
@@ -524,15 +558,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) tick_decode_persist_kernel(cons
               if (tm) w_ex += clock64() - t0;
               ptx::fence_proxy_async_all();
             }
-            if (STREAM) {
-              // one arrival per stage (the barrier counts two: this thread and the weight producer), all bytes announced with it
-              if (kb % kstep == 0) ptx::mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(kstep * GP_KB_BYTES));
-              ptx::tma_load_2d(smem + stage * SST_BYTES + (kb % kstep) * GP_KB_BYTES, tmap, &s_full[stage], kb * 64, coord);
-              if (kb % kstep == kstep - 1 && ++stage == SSTAGES) { stage = 0; phase ^= 1; }
-            } else {
-              ptx::mbar_arrive_expect_tx(&a_full[kb], GP_KB_BYTES);
-              ptx::tma_load_2d(sA + kb * GP_KB_BYTES, tmap, &a_full[kb], kb * 64, coord);
-            }
+            ptx::mbar_arrive_expect_tx(&a_full[kb], GP_KB_BYTES);
+            ptx::tma_load_2d(sA + kb * GP_KB_BYTES, tmap, &a_full[kb], kb * 64, coord);
             if (kb == 0) tr(3, ttr, kind * 4 + 1);
           }
           tr(3, ttr, kind * 4 + 2);

@@ -1,3 +1,3 @@
-for d in 0 1 4 8 13; do NOTIMING=1 NOSAVE=1 B=9472 NDIR=2 IPN_GPF_DBG=$d timeout 120 python tests/dev/persist_time.py 2>&1 | grep "dbg=" | cut -c1-200; done
-NOTIMING=1 NOSAVE=0 B=9472 NDIR=2 timeout 120 python tests/dev/persist_time.py 2>&1 | grep "dbg=" | cut -c1-200
-timeout 200 python -m pytest tests/test_gpu_tick_persist.py -x -q -m gpu 2>&1 | tail -1
+# forward layer kernel, training encoder shape (B=4096, 2 directions: CTA pairs inside the column split): step period from
+# the cycle stamps with A-loader ablations (IPN_GPF_DBG 32: no fence.proxy.async per k-block, 64: cta-scope barrier wait)
+for d in 0 32 64 96; do echo "=== IPN_GPF_DBG=$d"; IPN_GPF_DBG=$d B=4096 NDIR=2 timeout 200 python tests/dev/persist_time.py 2>&1 | grep "aload kb0\|aload kb7\|mma c0 issued\|dbg=" | cut -c1-120; done
