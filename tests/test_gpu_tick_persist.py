@@ -78,10 +78,13 @@ def test_persistent_tick_decode_matches_per_tick_path_and_oracle(V, H, train):
     sd = recipe.make_state_dict(recipe.mvae_spec(V, 10, H, Z), 4321)
     a = _decode(sd, V, H, B, train, persist=True)
     b = _decode(sd, V, H, B, train, persist=False)
-    # the first form of the kernel (resident A tile, weights alone in the ring: IPN_TICK_STREAM=0) issues the same MMAs in
-    # the same order on the same operands: bit-identical outputs
+    # the first form of the kernel (resident A tile, weights alone in the ring: IPN_TICK_STREAM=0) computes the same
+    # products; the streamed form takes the k-blocks in production order (chunks 0,2,4,6,1,3,5,7), so the fp32 sums
+    # differ in the last bits and an occasional h rounds to the neighbouring bf16: logits within 5e-3 (measured 1e-3) on
+    # the measures whose token paths coincide, nearly all of them (measured 0.996)
     a0 = _decode(sd, V, H, B, train, persist=True, stream=False)
-    assert torch.equal(a0["s"], a["s"]) and torch.equal(a0["w"], a["w"])
+    same0 = (a0["s"] == a["s"]).all(2).all(1)
+    assert same0.float().mean().item() > 0.9 and rel_err(a0["w"][same0], a["w"][same0]) < 5e-3
     # one launch (+ the table fold) instead of 24 x 5
     assert a["launches"] + 100 < b["launches"], (a["launches"], b["launches"])
     same = (a["s"] == b["s"]).all(2).all(1)
